@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of yahr_b200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one full frame of the workload: every primary ray of the image plus the shadow rays the
+reference's integrator needs (Integrators.hs:59).  Metric: Mrays/s (primary + shadow), whole job.
+  value : frame rendered with the scene resident in HBM and the frame left in HBM (rank 0)
+  e2e   : the same frame through the host-buffer C-ABI call (yahr_b200_render): kernel parameters
+          up, frame down to pinned host memory, inside the timed region
+The reference arm (--impl reference) times the CPU oracle port of the reference's render loop,
+tiles as OpenMP tasks on all host cores (the GHC reference cannot be built in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow)"
+UNIT = "Mrays/s"
+
+# Algorithmic bytes per ray of each workload under the REFERENCE's own traversal:
+#   32 B per box test + 36 B per triangle test + 36 B per triangle candidate (normals)
+#   + 16 B per sphere test + 28 B per material fetch + 24 B per light fetch + 12 B per primary ray,
+# counted by the oracle over the full frame (tools/count_bytes_per_ray.py; table in DESIGN.md).
+def _load_bytes_per_ray():
+    p = os.path.join(ROOT, "tools", "bytes_per_ray.json")
+    try:
+        return {k: float(v["bytes_per_ray"]) for k, v in json.load(open(p)).items()}
+    except Exception:
+        return {}
+
+
+BYTES_PER_RAY = _load_bytes_per_ray()   # committed output of tools/count_bytes_per_ray.py
+
+
+def workload(name):
+    from yahr_b200 import scenes
+    if name == "c4-terrain":
+        sc, cam = scenes.c4_terrain()
+        desc = "C4: 1M-triangle terrain (1001x501 height field), 3840x2160, 1 spp, 1 point light, BVH 32 Midpoint, depth 1"
+    elif name == "c4-soup":
+        sc, cam = scenes.c4_soup()
+        desc = "C4: 1M-triangle random soup, 3840x2160, 1 spp, 1 point light, BVH 32 Midpoint, depth 1"
+    elif name == "c3":
+        sc, cam = scenes.c3_sphere_grid()
+        desc = "C3: 32^3 sphere grid, 2048x2048, 1 point light, BVH 16 Midpoint, depth 1"
+    elif name == "c2":
+        sc, cam = scenes.c2_bunny_proxy()
+        desc = "C2: bunny proxy (69 566 triangles) + floor, 1920x1080, 1 point light, BVH 24 Midpoint, depth 1"
+    elif name == "c1":
+        sc, cam = scenes.c1_scene_yahrr()
+        desc = "C1: corrected scene.yahrr (7 spheres + floor), 512x512, 1 spp, BVH 16 Midpoint, depth 1"
+    elif name == "c5":
+        sc, cam = scenes.c5_replicated_bunny()
+        desc = "C5: 144 copies of the bunny proxy (10M triangles), 3840x2160, BVH 40 Midpoint, depth 1"
+    else:
+        raise SystemExit("unknown workload " + name)
+    return sc, cam, desc
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_run(sc, cam, target_seconds=15.0, threads=0, steps=1, warmup=0):
+    """Times the CPU oracle port on a bounded sample of the workload's tiles, all host threads.
+    Returns (dict, oracle stats of the last run)."""
+    from oracle import binding as ob
+    from yahr_b200 import api
+    w, h = api.image_size(cam)
+    t0 = time.time()
+    o = ob.OracleScene(sc)
+    build_s = time.time() - t0
+    n_tiles = int(ob.lib().yo_num_batches(1, w, h))
+    # calibrate on a thin sample, then choose a stride so one step is about target_seconds
+    stride = max(1, n_tiles // 64)
+    out = (np.zeros((h, w, 3), np.float32), np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32))
+    _, _, _, st = o.render(cam, threads=threads, tile_stride=stride, tile_offset=stride // 2, out=out)
+    per_tile = st["seconds"] / max(st["tiles"], 1)
+    want_tiles = max(8, int(target_seconds / max(per_tile, 1e-9)))
+    stride = max(1, n_tiles // want_tiles)
+    vals, last = [], None
+    for i in range(warmup + steps):
+        _, _, _, st = o.render(cam, threads=threads, tile_stride=stride, tile_offset=stride // 2, out=out)
+        rays = st["n_primary"] + st["n_shadow"] + st["n_secondary"]
+        if i >= warmup:
+            vals.append((rays / st["seconds"] / 1e6, st["seconds"]))
+        last = st
+    o.close()
+    bpr, rays, _ = ob.bytes_per_ray(last)
+    v = float(np.mean([x[0] for x in vals]))
+    sample = ("%d of %d reference tiles (every %dth, %d rays) of the same frame; oracle C++ port of the reference, "
+              "tiles as OpenMP dynamic tasks (renderPar analogue); BVH build %.1f s excluded"
+              % (last["tiles"], n_tiles, stride, rays, build_s))
+    d = {"value": v, "unit": UNIT, "cores": int(last["threads"]), "kind": "port", "sample": sample,
+         "seconds_per_step": float(np.mean([x[1] for x in vals])), "bytes_per_ray_sample": bpr,
+         "frames_per_s_extrapolated": v * 1e6 / (rays / last["tiles"] * n_tiles) if rays else None}
+    return d, last
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sc, cam, desc = workload(args.workload)
+    d, _ = cpu_baseline_run(sc, cam, target_seconds=args.cpu_seconds, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": d["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": d["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "name": args.workload},
+            "cpu_baseline": {k: d[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": d["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "GHC reference cannot be built in this image (no ghc/cabal); this is the restated C++ oracle port"}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from yahr_b200 import api
+    from yahr_b200.dist import TileShardedRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: yahr_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.build_library()
+    sc, cam, desc = workload(args.workload)
+    w, h = api.image_size(cam)
+    trav = api.TRAVERSAL_ORDERED if args.traversal == "ordered" else api.TRAVERSAL_REFERENCE
+
+    t0 = time.time()
+    R = TileShardedRenderer(sc, cam, mode=args.exchange)
+    create_s = time.time() - t0
+    info = R.scene.info()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ray counts and kernel-only time of this rank's share (library stats, synchronous)
+    st = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+    rays_local = st["n_primary"] + st["n_shadow"] + st["n_secondary"]
+    rays_t = torch.tensor([rays_local, st["n_primary"], st["n_shadow"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rays_t)
+    rays_total, n_primary, n_shadow = (float(x) for x in rays_t.tolist())
+    launches_per_step = st["launches"]
+
+    # ---- value: device-resident ------------------------------------------------------------
+    for _ in range(args.warmup):
+        R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()                                    # L2 flush between timed iterations
+            if world > 1:
+                dist.barrier()
+            ev[i][0].record()
+            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            ev[i][1].record()
+        barrier()
+        # kernel-only time of the dominant kernel, measured live with CUDA events (library stats)
+        for i in range(min(args.steps, 5)):
+            flush.zero_()
+            stk = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            kernel_ms.append(stk["gpu_ms"])
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)       # max over ranks, per step
+    ms_per_step = float(step_ms.mean())
+    value = rays_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer C-ABI call, pinned output, copies inside the timed region ----------
+    e2e = None
+    if world == 1:
+        host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+        out = (host_rgb.numpy(), None)
+        for _ in range(max(1, args.warmup)):
+            _, _, ste = R.scene.render(cam, recursion_depth=args.depth, spp=args.spp, want_primid=False, out=out)
+        times = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            _, _, ste = R.scene.render(cam, recursion_depth=args.depth, spp=args.spp, want_primid=False, out=out)
+            times.append(time.perf_counter() - t)
+        e2e_ms = float(np.mean(times)) * 1e3
+        e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(ste["h2d_bytes"]), "d2h_bytes_per_step": int(ste["d2h_bytes"]),
+               "api": "yahr_b200_render (host buffers; kernel parameters up, RGB32F frame down to pinned memory)",
+               "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
+    else:
+        host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+        times = []
+        for i in range(args.warmup + args.steps):
+            flush.zero_()
+            barrier()
+            t = time.perf_counter()
+            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            if rank == 0:
+                host_rgb.copy_(R.frame, non_blocking=True)
+            barrier()
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t)
+        tt = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt) * 1e3
+        e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 256, "d2h_bytes_per_step": int(w * h * 12),
+               "api": "TileShardedRenderer.render (%s exchange) + frame down to pinned memory on rank 0" % R.mode,
+               "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    peak, peak_src = peaks()
+    k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
+    bpr = BYTES_PER_RAY.get(args.workload)
+    roofline = None
+    if k_ms and bpr:
+        achieved = rays_local * bpr / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "k_render_mega", "kernel_ms": k_ms, "bytes_per_ray": bpr,
+                    "rays_per_launch": rays_local, "peak_source": peak_src,
+                    "note": "algorithmic bytes under the reference's traversal; traversal is latency/divergence "
+                            "bound, see DESIGN.md"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline_run(sc, cam, target_seconds=args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "bytes_per_ray_sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "name": args.workload, "rays_per_frame": rays_total,
+                           "primary": n_primary, "shadow": n_shadow, "traversal": args.traversal,
+                           "exchange": R.mode, "l2": "flushed between timed iterations (256 MiB write)",
+                           "bvh_nodes": info["n_nodes"], "bvh_depth": info["depth"],
+                           "scene_bytes": info["device_bytes"], "bvh_build_ms": info["build_ms"]},
+                "frames_per_s": 1e3 / ms_per_step, "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    R.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4-terrain")
+    ap.add_argument("--traversal", default="reference", choices=["reference", "ordered"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "reduce"])
+    ap.add_argument("--depth", type=int, default=1)
+    ap.add_argument("--spp", type=int, default=1)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

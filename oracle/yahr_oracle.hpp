@@ -627,6 +627,7 @@ inline int64_t roundUpPow2(int64_t x) {
 // parses as  ((max (32*numThreads) width) * height) `div` 256
 inline int64_t numBatches(int64_t numThreads, int64_t width, int64_t height) {
   int64_t m = (32 * numThreads > width) ? 32 * numThreads : width;
+  if ((m * height) / 256 < 1) return 1;   // the reference dies here (2 ^ negative); one tile instead
   return roundUpPow2((m * height) / 256);
 }
 

@@ -1,0 +1,324 @@
+"""ctypes binding of libyahr_b200.so (include/yahr_b200.h).
+
+This is plumbing: every render goes through the C ABI into the CUDA kernels.  There is no CPU
+fallback -- a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyahr_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+
+TRAVERSAL_REFERENCE = 0
+TRAVERSAL_ORDERED = 1
+PRIM_MISS = 0xFFFFFFFF
+
+
+class YahrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("yahr_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("n_triangles", C.c_uint32),
+        ("tri_p0", _f32p), ("tri_p1", _f32p), ("tri_p2", _f32p),
+        ("tri_n0", _f32p), ("tri_n1", _f32p), ("tri_n2", _f32p),
+        ("tri_material", _u32p),
+        ("n_spheres", C.c_uint32),
+        ("sph_center", _f32p), ("sph_radius", _f32p), ("sph_material", _u32p),
+        ("prim_order", _u32p),
+        ("n_materials", C.c_uint32), ("materials", _f32p),
+        ("n_lights", C.c_uint32), ("lights", _f32p),
+        ("bvh_max_depth", C.c_int32), ("split_mode", C.c_int32),
+    ]
+
+
+class Camera(C.Structure):
+    _fields_ = [("imW", C.c_float), ("imH", C.c_float), ("focalLength", C.c_float),
+                ("lookDir", C.c_float * 3), ("upDir", C.c_float * 3), ("position", C.c_float * 3)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("recursion_depth", C.c_int32), ("spp", C.c_int32), ("seed", C.c_uint64),
+                ("traversal", C.c_int32), ("tile_stride", C.c_int32), ("tile_offset", C.c_int32),
+                ("kernel", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_primary", C.c_uint64), ("n_shadow", C.c_uint64), ("n_secondary", C.c_uint64),
+                ("gpu_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("tiles", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_primitives", C.c_uint32), ("n_nodes", C.c_uint32), ("n_multi_leaves", C.c_uint32),
+                ("depth", C.c_uint32), ("device_bytes", C.c_uint64), ("build_ms", C.c_double),
+                ("upload_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build_library(force=False):
+    """Compile libyahr_b200.so in-tree with nvcc for sm_100a (no GPU needed to build)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cpp", ".hpp", ".cuh")) or f == "Makefile"]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "yahr_b200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libyahr_b200.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` or `make -C yahr_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.yahr_b200_abi_version.restype = C.c_int
+    L.yahr_b200_device_count.restype = C.c_int
+    L.yahr_b200_last_error.restype = C.c_char_p
+    L.yahr_b200_scene_create.restype = C.c_int
+    L.yahr_b200_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+    L.yahr_b200_scene_destroy.argtypes = [C.c_void_p]
+    L.yahr_b200_scene_info.restype = C.c_int
+    L.yahr_b200_scene_info.argtypes = [C.c_void_p, C.POINTER(SceneInfo)]
+    L.yahr_b200_render.restype = C.c_int
+    L.yahr_b200_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                   C.c_void_p, C.POINTER(Stats)]
+    L.yahr_b200_render_device.restype = C.c_int
+    L.yahr_b200_render_device.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    L.yahr_b200_num_batches.restype = C.c_int64
+    L.yahr_b200_num_batches.argtypes = [C.c_int64] * 3
+    L.yahr_b200_batch_window.restype = C.c_int
+    L.yahr_b200_batch_window.argtypes = [C.c_int64] * 4 + [C.POINTER(C.c_int32)]
+    L.yahr_b200_ipc_export.restype = C.c_int
+    L.yahr_b200_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.yahr_b200_ipc_open.restype = C.c_int
+    L.yahr_b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.yahr_b200_ipc_close.restype = C.c_int
+    L.yahr_b200_ipc_close.argtypes = [C.c_void_p]
+    L.yahr_b200_host_bvh_build.restype = C.c_int
+    L.yahr_b200_host_bvh_build.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+    L.yahr_b200_host_bvh_destroy.argtypes = [C.c_void_p]
+    for n in ("num_primitives", "num_nodes", "depth"):
+        f = getattr(L, "yahr_b200_host_bvh_" + n)
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_void_p]
+    L.yahr_b200_host_bvh_order.restype = C.c_int
+    L.yahr_b200_host_bvh_order.argtypes = [C.c_void_p, _u32p]
+    L.yahr_b200_host_bvh_preorder.restype = C.c_int
+    L.yahr_b200_host_bvh_preorder.argtypes = [C.c_void_p, _u32p, _u32p, _u32p, _f32p]
+    L.yahr_b200_camera_matrices.restype = C.c_int
+    L.yahr_b200_camera_matrices.argtypes = [C.POINTER(Camera), _f32p, _f32p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise YahrError(rc, lib().yahr_b200_last_error().decode("utf-8", "replace"))
+
+
+def _get(obj, name, default=None):
+    if isinstance(obj, dict):
+        return obj.get(name, default)
+    return getattr(obj, name, default)
+
+
+def scene_desc(scene):
+    """dict/object of numpy arrays -> (SceneDesc, keepalive)."""
+    keep = []
+
+    def fp(name, cols):
+        a = _get(scene, name)
+        if a is None or len(a) == 0:
+            return None, 0
+        arr = np.asarray(a, dtype=np.float32)
+        arr = np.ascontiguousarray(arr.reshape(-1, cols) if cols else arr.reshape(-1))
+        keep.append(arr)
+        return arr.ctypes.data_as(_f32p), arr.shape[0]
+
+    def up(name, n):
+        a = _get(scene, name)
+        if a is None or n == 0:
+            return None
+        arr = np.ascontiguousarray(np.asarray(a, dtype=np.uint32).reshape(-1))
+        if arr.shape[0] != n:
+            raise ValueError("%s has %d entries, expected %d" % (name, arr.shape[0], n))
+        keep.append(arr)
+        return arr.ctypes.data_as(_u32p)
+
+    d = SceneDesc()
+    d.tri_p0, nt = fp("tri_p0", 3)
+    for nme in ("tri_p1", "tri_p2", "tri_n0", "tri_n1", "tri_n2"):
+        p, n = fp(nme, 3)
+        if n != nt:
+            raise ValueError("%s has %d rows, expected %d" % (nme, n, nt))
+        setattr(d, nme, p)
+    d.n_triangles = nt
+    d.tri_material = up("tri_material", nt)
+    d.sph_center, ns = fp("sph_center", 3)
+    d.sph_radius, nr = fp("sph_radius", 0)
+    if nr != ns:
+        raise ValueError("sph_radius has %d entries, expected %d" % (nr, ns))
+    d.n_spheres = ns
+    d.sph_material = up("sph_material", ns)
+    d.prim_order = up("prim_order", nt + ns) if _get(scene, "prim_order") is not None else None
+    d.materials, d.n_materials = fp("materials", 7)
+    d.lights, d.n_lights = fp("lights", 6)
+    d.bvh_max_depth = int(_get(scene, "bvh_max_depth", 16))
+    d.split_mode = int(_get(scene, "split_mode", 0))
+    return d, keep
+
+
+def make_camera(cam):
+    c = Camera()
+    c.imW, c.imH, c.focalLength = float(_get(cam, "imW")), float(_get(cam, "imH")), float(_get(cam, "focalLength"))
+    for n in ("lookDir", "upDir", "position"):
+        v = _get(cam, n)
+        getattr(c, n)[:] = [float(v[0]), float(v[1]), float(v[2])]
+    return c
+
+
+def image_size(cam):
+    c = make_camera(cam)
+    return int(np.floor(c.imW)), int(np.floor(c.imH))
+
+
+def device_count():
+    return lib().yahr_b200_device_count()
+
+
+class Scene:
+    """A scene resident on the current CUDA device (BVH built and uploaded once)."""
+
+    def __init__(self, scene):
+        L = lib()
+        d, keep = scene_desc(scene)
+        h = C.c_void_p()
+        _check(L.yahr_b200_scene_create(C.byref(d), C.byref(h)))
+        self._h = h
+        del keep
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().yahr_b200_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        i = SceneInfo()
+        _check(lib().yahr_b200_scene_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def render(self, cam, recursion_depth=1, spp=1, seed=0, want_primid=True, out=None):
+        """Host-buffer entry (yahr_b200_render).  Returns (rgb[H,W,3], primid[H,W] or None, stats)."""
+        c = make_camera(cam)
+        w, h = int(np.floor(c.imW)), int(np.floor(c.imH))
+        if out is None:
+            rgb = np.empty((h, w, 3), np.float32)
+            pid = np.empty((h, w), np.uint32) if want_primid else None
+        else:
+            rgb, pid = out
+        st = Stats()
+        _check(lib().yahr_b200_render(self._h, C.byref(c), recursion_depth, spp, seed, rgb.ctypes.data,
+                                      pid.ctypes.data if pid is not None else None, C.byref(st)))
+        return rgb, pid, st.as_dict()
+
+    def render_device(self, cam, d_rgb, d_primid=None, recursion_depth=1, spp=1, seed=0,
+                      traversal=TRAVERSAL_REFERENCE, tile_stride=1, tile_offset=0, stream=None, stats=True,
+                      kernel=0):
+        """Device-buffer entry (yahr_b200_render_device).  d_rgb / d_primid are raw device pointers
+        (ints), e.g. torch_tensor.data_ptr().  Returns a stats dict (synchronises) or None."""
+        c = make_camera(cam)
+        o = RenderOpts()
+        o.recursion_depth, o.spp, o.seed = recursion_depth, spp, seed
+        o.traversal, o.tile_stride, o.tile_offset, o.kernel = traversal, tile_stride, tile_offset, kernel
+        st = Stats() if stats else None
+        _check(lib().yahr_b200_render_device(self._h, C.byref(c), C.byref(o), C.c_void_p(d_rgb),
+                                             C.c_void_p(d_primid) if d_primid else None,
+                                             C.c_void_p(stream) if stream else None,
+                                             C.byref(st) if stats else None))
+        return st.as_dict() if stats else None
+
+
+class HostBvh:
+    """Host-only view of the BVH the library would upload (no CUDA needed)."""
+
+    def __init__(self, scene):
+        d, keep = scene_desc(scene)
+        h = C.c_void_p()
+        _check(lib().yahr_b200_host_bvh_build(C.byref(d), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().yahr_b200_host_bvh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def depth(self):
+        return lib().yahr_b200_host_bvh_depth(self._h)
+
+    def order(self):
+        n = lib().yahr_b200_host_bvh_num_primitives(self._h)
+        out = np.zeros(n, np.uint32)
+        _check(lib().yahr_b200_host_bvh_order(self._h, out.ctypes.data_as(_u32p)))
+        return out
+
+    def preorder(self):
+        n = lib().yahr_b200_host_bvh_num_nodes(self._h)
+        kinds, firsts, counts = (np.zeros(n, np.uint32) for _ in range(3))
+        boxes = np.zeros((n, 6), np.float32)
+        _check(lib().yahr_b200_host_bvh_preorder(self._h, kinds.ctypes.data_as(_u32p), firsts.ctypes.data_as(_u32p),
+                                                 counts.ctypes.data_as(_u32p), boxes.ctypes.data_as(_f32p)))
+        return kinds, firsts, counts, boxes
+
+
+def camera_matrices(cam):
+    c = make_camera(cam)
+    tf = np.zeros(16, np.float32)
+    vtf = np.zeros(16, np.float32)
+    _check(lib().yahr_b200_camera_matrices(C.byref(c), tf.ctypes.data_as(_f32p), vtf.ctypes.data_as(_f32p)))
+    return tf.reshape(4, 4), vtf.reshape(4, 4)
+
+
+def num_batches(num_threads, w, h):
+    return lib().yahr_b200_num_batches(num_threads, w, h)
+
+
+def batch_window(w, h, num, count):
+    out = (C.c_int32 * 4)()
+    _check(lib().yahr_b200_batch_window(w, h, num, count, out))
+    return tuple(out)

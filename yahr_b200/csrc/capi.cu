@@ -1,0 +1,443 @@
+// capi.cu -- the C ABI of libyahr_b200.so (include/yahr_b200.h).  No CPU fallback: every compute
+// entry point needs a CUDA device and fails with YAHR_ERR_NO_DEVICE / YAHR_ERR_CUDA otherwise.
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/yahr_b200.h"
+#include "bvh_build.hpp"
+#include "device_types.cuh"
+#include "host_scene.hpp"
+#include "kernels.hpp"
+
+using namespace yb;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+  g_lastError = msg;
+  return code;
+}
+
+struct CudaFailure { cudaError_t e; const char* what; const char* file; int line; };
+
+#define CU(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) throw CudaFailure{e__, #call, __FILE__, __LINE__}; \
+  } while (0)
+
+int cudaFail(const CudaFailure& f) {
+  int code = f.e == cudaErrorMemoryAllocation ? YAHR_ERR_OUT_OF_MEMORY
+             : (f.e == cudaErrorNoDevice || f.e == cudaErrorInsufficientDriver) ? YAHR_ERR_NO_DEVICE
+                                                                                : YAHR_ERR_CUDA;
+  return fail(code, std::string("CUDA error: ") + cudaGetErrorString(f.e) + " in " + f.what + " (" + f.file + ":" +
+                        std::to_string(f.line) + ")");
+}
+
+double nowMs() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+T* devUpload(const std::vector<T>& v, uint64_t& bytes) {
+  if (v.empty()) return nullptr;
+  T* p = nullptr;
+  CU(cudaMalloc(&p, v.size() * sizeof(T)));
+  CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  bytes += v.size() * sizeof(T);
+  return p;
+}
+
+struct TileSet { int4* d_tiles = nullptr; uint32_t n = 0; };
+
+}  // namespace
+
+struct yahr_scene {
+  int device = 0;
+  DeviceScene dev{};
+  float4* d_nodes = nullptr;
+  float4* d_prims = nullptr;
+  float4* d_normals = nullptr;
+  uint2* d_multi = nullptr;
+  float4* d_materials = nullptr;
+  float4* d_lights = nullptr;
+  unsigned long long* d_counters = nullptr;
+  yahr_scene_info info{};
+  // per (width, height, stride, offset) tile lists, uploaded once
+  std::map<std::tuple<int, int, int, int>, TileSet> tiles;
+  // frame buffers of the host-buffer entry (grown on demand)
+  float* d_rgb = nullptr;
+  uint32_t* d_primid = nullptr;
+  size_t framePixels = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  ~yahr_scene() {
+    cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
+    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid);
+    for (auto& kv : tiles) cudaFree(kv.second.d_tiles);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+struct yahr_host_bvh {
+  HostBvh bvh;
+};
+
+namespace {
+
+const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
+  auto key = std::make_tuple(w, h, stride, offset);
+  auto it = sc->tiles.find(key);
+  if (it != sc->tiles.end()) return it->second;
+  // samplePoints = squareBatches width height nBatches (main.hs:128-131).  numThreads only enters
+  // through max (32 * numThreads) width; the GPU path uses 1 (tiles are a scheduling unit, the
+  // image does not depend on them).
+  const int64_t nBatches = numBatches(1, w, h);
+  std::vector<int4> host;
+  for (int64_t b = offset; b < nBatches; b += stride) {
+    TileWindow t = batchWindow(w, h, b, nBatches);
+    if (t.x1 > t.x0 && t.y1 > t.y0) host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
+  }
+  TileSet ts;
+  ts.n = (uint32_t)host.size();
+  uint64_t bytes = 0;
+  ts.d_tiles = devUpload(host, bytes);
+  return sc->tiles.emplace(key, ts).first->second;
+}
+
+int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb,
+                 uint32_t* d_primid, cudaStream_t stream, yahr_stats* stats, bool sync) {
+  CameraSetup cs;
+  std::string err;
+  int rc = setupCamera(cam, cs, err);
+  if (rc) return fail(rc, err);
+  if (opts->spp < 1) return fail(YAHR_ERR_INVALID_ARGUMENT, "spp must be >= 1");
+  if (opts->recursion_depth < 0 || opts->recursion_depth > YAHR_B200_MAX_RECURSION)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "recursion_depth out of range [0, 16]");
+  if (opts->tile_stride < 1 || opts->tile_offset < 0 || opts->tile_offset >= opts->tile_stride)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "tile_stride/tile_offset invalid");
+  if (opts->traversal != YAHR_TRAVERSAL_REFERENCE && opts->traversal != YAHR_TRAVERSAL_ORDERED)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "unknown traversal mode");
+
+  const double w0 = nowMs();
+  const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset);
+  RenderParams P{};
+  P.sc = sc->dev;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) P.vtf[4 * i + j] = cs.vtf.m[i][j];
+  for (int i = 0; i < 3; ++i) P.origin[i] = cs.origin[i];
+  P.focal = cam->focalLength;
+  P.width = cs.width; P.height = cs.height;
+  P.depth = opts->recursion_depth; P.spp = opts->spp; P.seed = opts->seed;
+  P.traversal = opts->traversal;
+  P.tiles = ts.d_tiles; P.nTiles = ts.n;
+  P.rgb = d_rgb; P.primid = d_primid;
+  P.counters = sc->d_counters;
+
+  uint32_t launches = 0;
+  CU(cudaMemsetAsync(sc->d_counters, 0, 3 * sizeof(unsigned long long), stream));
+  if (stats) CU(cudaEventRecord(sc->ev0, stream));
+  CU(launchRenderMega(P, stream, &launches));
+  if (stats) CU(cudaEventRecord(sc->ev1, stream));
+  if (stats) {
+    unsigned long long c[3];
+    CU(cudaMemcpyAsync(c, sc->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
+    stats->gpu_ms = ms;
+    stats->launches = launches;
+    stats->tiles = ts.n;
+    stats->wall_ms = nowMs() - w0;
+  } else if (sync) {
+    CU(cudaStreamSynchronize(stream));
+  }
+  return YAHR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yahr_b200_abi_version(void) { return YAHR_B200_ABI_VERSION; }
+
+int yahr_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* yahr_b200_last_error(void) { return g_lastError.c_str(); }
+
+int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
+  if (!out) return fail(YAHR_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  yahr_scene* sc = nullptr;
+  try {
+    if (yahr_b200_device_count() < 1)
+      return fail(YAHR_ERR_NO_DEVICE, "no CUDA device available (libyahr_b200 has no CPU fallback)");
+    std::vector<HostPrim> prims;
+    std::vector<Box> bounds;
+    std::string err;
+    int rc = gatherPrimitives(desc, prims, bounds, err);
+    if (rc) return fail(rc, err);
+
+    const double t0 = nowMs();
+    HostBvh bvh;
+    buildReferenceBvh(bounds, desc->bvh_max_depth, desc->split_mode, bvh);
+    const double t1 = nowMs();
+    if (bvh.maxStack > YAHR_B200_MAX_STACK)
+      return fail(YAHR_ERR_BVH_TOO_DEEP, "BVH depth " + std::to_string(bvh.depth) + " exceeds the traversal stack (" +
+                                             std::to_string(YAHR_B200_MAX_STACK) + ")");
+
+    // primitives and normals in DFS leaf order
+    const size_t n = prims.size();
+    std::vector<float4> recs(3 * n), nrm(3 * n);
+    auto bits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t id = bvh.order[i];
+      const HostPrim& p = prims[id];
+      const float meta = bits((p.material << 1) | (p.kind & 1u));
+      if (p.kind == 1) {
+        const f3 e1 = p.b - p.a, e2 = p.c - p.a;                     // Shapes.hs:38-39
+        recs[3 * i + 0] = make_float4(p.a.x, p.a.y, p.a.z, meta);
+        recs[3 * i + 1] = make_float4(e1.x, e1.y, e1.z, bits(id));
+        recs[3 * i + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+        nrm[3 * i + 0] = make_float4(p.n0.x, p.n0.y, p.n0.z, 0.0f);
+        nrm[3 * i + 1] = make_float4(p.n1.x, p.n1.y, p.n1.z, 0.0f);
+        nrm[3 * i + 2] = make_float4(p.n2.x, p.n2.y, p.n2.z, 0.0f);
+      } else {
+        recs[3 * i + 0] = make_float4(p.a.x, p.a.y, p.a.z, meta);
+        recs[3 * i + 1] = make_float4(p.radius, 0.0f, 0.0f, bits(id));
+        recs[3 * i + 2] = make_float4(0, 0, 0, 0);
+        nrm[3 * i + 0] = nrm[3 * i + 1] = nrm[3 * i + 2] = make_float4(0, 0, 0, 0);
+      }
+    }
+    std::vector<float4> mats(2 * (size_t)desc->n_materials), lights(2 * (size_t)desc->n_lights);
+    for (uint32_t m = 0; m < desc->n_materials; ++m) {
+      const float* s = desc->materials + 7 * (size_t)m;
+      mats[2 * m + 0] = make_float4(s[0], s[1], s[2], s[6]);
+      mats[2 * m + 1] = make_float4(s[3], s[4], s[5], 0.0f);
+    }
+    for (uint32_t l = 0; l < desc->n_lights; ++l) {
+      const float* s = desc->lights + 6 * (size_t)l;
+      lights[2 * l + 0] = make_float4(s[0], s[1], s[2], 0.0f);
+      lights[2 * l + 1] = make_float4(s[3], s[4], s[5], 0.0f);
+    }
+    std::vector<uint2> multi(bvh.multiLeaves.size() / 2);
+    for (size_t k = 0; k < multi.size(); ++k) multi[k] = make_uint2(bvh.multiLeaves[2 * k], bvh.multiLeaves[2 * k + 1]);
+
+    sc = new yahr_scene();
+    CU(cudaGetDevice(&sc->device));
+    const double t2 = nowMs();
+    uint64_t bytes = 0;
+    static_assert(sizeof(FlatNode) == 4 * sizeof(float4), "node layout");
+    if (!bvh.flat.empty()) {
+      CU(cudaMalloc(&sc->d_nodes, bvh.flat.size() * sizeof(FlatNode)));
+      CU(cudaMemcpy(sc->d_nodes, bvh.flat.data(), bvh.flat.size() * sizeof(FlatNode), cudaMemcpyHostToDevice));
+      bytes += bvh.flat.size() * sizeof(FlatNode);
+    }
+    sc->d_prims = devUpload(recs, bytes);
+    sc->d_normals = devUpload(nrm, bytes);
+    sc->d_multi = devUpload(multi, bytes);
+    sc->d_materials = devUpload(mats, bytes);
+    sc->d_lights = devUpload(lights, bytes);
+    CU(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
+    CU(cudaEventCreate(&sc->ev0));
+    CU(cudaEventCreate(&sc->ev1));
+    CU(cudaDeviceSynchronize());
+    const double t3 = nowMs();
+
+    sc->dev.nodes = sc->d_nodes; sc->dev.prims = sc->d_prims; sc->dev.normals = sc->d_normals;
+    sc->dev.multiLeaves = sc->d_multi; sc->dev.materials = sc->d_materials; sc->dev.lights = sc->d_lights;
+    sc->dev.nLights = desc->n_lights;
+    sc->dev.rootRef = bvh.rootRef;
+    sc->dev.rootLo[0] = bvh.rootBox.lo.x; sc->dev.rootLo[1] = bvh.rootBox.lo.y; sc->dev.rootLo[2] = bvh.rootBox.lo.z;
+    sc->dev.rootHi[0] = bvh.rootBox.hi.x; sc->dev.rootHi[1] = bvh.rootBox.hi.y; sc->dev.rootHi[2] = bvh.rootBox.hi.z;
+    sc->info.n_primitives = (uint32_t)n;
+    sc->info.n_nodes = (uint32_t)bvh.flat.size();
+    sc->info.n_multi_leaves = (uint32_t)multi.size();
+    sc->info.depth = bvh.depth;
+    sc->info.device_bytes = bytes;
+    sc->info.build_ms = t1 - t0;
+    sc->info.upload_ms = t3 - t2;
+    *out = sc;
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    delete sc;
+    return cudaFail(f);
+  } catch (const std::bad_alloc&) {
+    delete sc;
+    return fail(YAHR_ERR_OUT_OF_MEMORY, "host out of memory");
+  } catch (const std::exception& e) {
+    delete sc;
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+
+void yahr_b200_scene_destroy(yahr_scene* scene) {
+  if (!scene) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(scene->device);
+  delete scene;
+  cudaSetDevice(prev);
+}
+
+int yahr_b200_scene_info(const yahr_scene* scene, yahr_scene_info* out) {
+  if (!scene || !out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = scene->info;
+  return YAHR_OK;
+}
+
+int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb,
+                            uint32_t* d_primid, void* stream, yahr_stats* stats) {
+  if (!scene || !cam || !opts || !d_rgb) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  try {
+    return renderCommon(scene, cam, opts, d_rgb, d_primid, (cudaStream_t)stream, stats, false);
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  } catch (const std::exception& e) {
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+
+int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                     float* rgb_out, uint32_t* primid_out, yahr_stats* stats) {
+  if (!scene || !cam || !rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  try {
+    const double w0 = nowMs();
+    CameraSetup cs;
+    std::string err;
+    int rc = setupCamera(cam, cs, err);
+    if (rc) return fail(rc, err);
+    const size_t px = (size_t)cs.width * cs.height;
+    if (px > scene->framePixels) {
+      cudaFree(scene->d_rgb); cudaFree(scene->d_primid);
+      scene->d_rgb = nullptr; scene->d_primid = nullptr; scene->framePixels = 0;
+      CU(cudaMalloc(&scene->d_rgb, px * 3 * sizeof(float)));
+      CU(cudaMalloc(&scene->d_primid, px * sizeof(uint32_t)));
+      scene->framePixels = px;
+    }
+    yahr_render_opts o{};
+    o.recursion_depth = recursion_depth; o.spp = spp; o.seed = seed;
+    o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = 1; o.tile_offset = 0;
+    yahr_stats local{};
+    rc = renderCommon(scene, cam, &o, scene->d_rgb, primid_out ? scene->d_primid : nullptr, nullptr, &local, true);
+    if (rc) return rc;
+    CU(cudaMemcpy(rgb_out, scene->d_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    local.d2h_bytes = px * 3 * sizeof(float);
+    if (primid_out) {
+      CU(cudaMemcpy(primid_out, scene->d_primid, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      local.d2h_bytes += px * sizeof(uint32_t);
+    }
+    local.h2d_bytes = sizeof(RenderParams);
+    local.wall_ms = nowMs() - w0;
+    if (stats) *stats = local;
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  } catch (const std::exception& e) {
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+
+int64_t yahr_b200_num_batches(int64_t num_threads, int64_t width, int64_t height) {
+  return numBatches(num_threads, width, height);
+}
+
+int yahr_b200_batch_window(int64_t width, int64_t height, int64_t num, int64_t count, int32_t out[4]) {
+  if (!out || count < 1 || num < 0 || num >= count || width < 1 || height < 1)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "batch_window: invalid argument");
+  TileWindow t = batchWindow(width, height, num, count);
+  out[0] = t.x0; out[1] = t.y0; out[2] = t.x1; out[3] = t.y1;
+  return YAHR_OK;
+}
+
+int yahr_b200_ipc_export(void* device_ptr, unsigned char handle_out[YAHR_B200_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == YAHR_B200_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!device_ptr || !handle_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, device_ptr);
+  if (e != cudaSuccess) return fail(YAHR_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return YAHR_OK;
+}
+
+int yahr_b200_ipc_open(const unsigned char handle[YAHR_B200_IPC_HANDLE_BYTES], void** device_ptr_out) {
+  if (!handle || !device_ptr_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(device_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(YAHR_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  return YAHR_OK;
+}
+
+int yahr_b200_ipc_close(void* device_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(device_ptr);
+  if (e != cudaSuccess) return fail(YAHR_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+  return YAHR_OK;
+}
+
+// ---- host-only inspection ----------------------------------------------------------------------
+int yahr_b200_host_bvh_build(const yahr_scene_desc* desc, yahr_host_bvh** out) {
+  if (!out) return fail(YAHR_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  try {
+    std::vector<HostPrim> prims;
+    std::vector<Box> bounds;
+    std::string err;
+    int rc = gatherPrimitives(desc, prims, bounds, err);
+    if (rc) return fail(rc, err);
+    yahr_host_bvh* h = new yahr_host_bvh();
+    buildReferenceBvh(bounds, desc->bvh_max_depth, desc->split_mode, h->bvh);
+    *out = h;
+    return YAHR_OK;
+  } catch (const std::exception& e) {
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+void yahr_b200_host_bvh_destroy(yahr_host_bvh* b) { delete b; }
+uint32_t yahr_b200_host_bvh_num_primitives(const yahr_host_bvh* b) { return b ? (uint32_t)b->bvh.order.size() : 0; }
+uint32_t yahr_b200_host_bvh_num_nodes(const yahr_host_bvh* b) { return b ? (uint32_t)b->bvh.nodes.size() : 0; }
+uint32_t yahr_b200_host_bvh_depth(const yahr_host_bvh* b) { return b ? b->bvh.depth : 0; }
+int yahr_b200_host_bvh_order(const yahr_host_bvh* b, uint32_t* order_out) {
+  if (!b || !order_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::memcpy(order_out, b->bvh.order.data(), b->bvh.order.size() * sizeof(uint32_t));
+  return YAHR_OK;
+}
+int yahr_b200_host_bvh_preorder(const yahr_host_bvh* b, uint32_t* kinds, uint32_t* firsts, uint32_t* counts,
+                                float* boxes6) {
+  if (!b || !kinds || !firsts || !counts || !boxes6) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (size_t i = 0; i < b->bvh.nodes.size(); ++i) {
+    const RefNode& n = b->bvh.nodes[i];
+    kinds[i] = n.kind; firsts[i] = n.first; counts[i] = n.kind == kInner ? 0 : n.count;
+    float* bx = boxes6 + 6 * i;
+    bx[0] = n.box.lo.x; bx[1] = n.box.lo.y; bx[2] = n.box.lo.z; bx[3] = n.box.hi.x; bx[4] = n.box.hi.y; bx[5] = n.box.hi.z;
+  }
+  return YAHR_OK;
+}
+int yahr_b200_camera_matrices(const yahr_camera* cam, float tf16[16], float vtf16[16]) {
+  CameraSetup cs;
+  std::string err;
+  int rc = setupCamera(cam, cs, err);
+  if (rc) return fail(rc, err);
+  std::memcpy(tf16, cs.tf.m, 64);
+  std::memcpy(vtf16, cs.vtf.m, 64);
+  return YAHR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// device_types.cuh -- data layout in HBM and the kernel parameter block (shared by host and device code).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace yb {
+
+// Flattened scene (see DESIGN.md "Data layout in HBM").
+//   nodes     : 4 x float4 per inner node  = {left box, right box, left ref, right ref}        64 B
+//   prims     : 3 x float4 per primitive in left-first DFS leaf order                          48 B
+//                 triangle: A = (p0.xyz, meta)  B = (e1.xyz, primitive ID)  C = (e2.xyz, 0)
+//                 sphere  : A = (c.xyz,  meta)  B = (r, 0, 0, primitive ID) C unused
+//                 meta = (material << 1) | kind   (kind 0 sphere, 1 triangle), as raw bits
+//               e1 = p1 - p0 and e2 = p2 - p0 are the reference's own first two operations
+//               (Shapes.hs:38-39) done once on the host in binary32.
+//   normals   : 3 x float4 per primitive (n0, n1, n2), same order; only read for triangle
+//               candidates that pass the barycentric / t tests                                 48 B
+//   multiLeaves : (first, count) per multi-leaf
+//   materials : 2 x float4 = (diffuse.rgb, shininess), (specular.rgb, 0)
+//   lights    : 2 x float4 = (position.xyz, 0), (spectrum.rgb, 0)
+struct DeviceScene {
+  const float4* nodes;
+  const float4* prims;
+  const float4* normals;
+  const uint2* multiLeaves;
+  const float4* materials;
+  const float4* lights;
+  uint32_t nLights;
+  uint32_t rootRef;
+  float rootLo[3], rootHi[3];
+};
+
+static const uint32_t kDevRefNull = 0xFFFFFFFFu;
+static const uint32_t kDevRefLeafBit = 0x80000000u;
+static const uint32_t kDevRefMultiBits = 0xC0000000u;
+
+struct RenderParams {
+  DeviceScene sc;
+  float vtf[12];          // rows 0..2 of vtf = tf !*! rasterToCamera (Cameras.hs:81)
+  float origin[3];        // transformPoint tf (0,0,0)              (Cameras.hs:84)
+  float focal;
+  int32_t width, height;
+  int32_t depth, spp;
+  uint64_t seed;
+  int32_t traversal;
+  const int4* tiles;      // windows (x0, y0, x1, y1) of the tiles rendered by this call
+  uint32_t nTiles;
+  float* rgb;             // W*H*3, may be peer memory
+  uint32_t* primid;       // W*H or nullptr
+  unsigned long long* counters;  // [0] primary, [1] shadow, [2] secondary
+};
+
+}  // namespace yb

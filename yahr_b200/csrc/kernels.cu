@@ -1,0 +1,65 @@
+// kernels.cu -- sm_100a kernels of libyahr_b200.  Compile with --fmad=false (bit-exact primitive IDs).
+#include "kernels.hpp"
+#include "render_device.cuh"
+
+namespace yb {
+
+using namespace dev;
+
+// ---------------------------------------------------------------------------------------------
+// Kernel "mega": one CTA per reference tile (the reference's unit of parallelism: one spark /
+// Par task per squareBatches window, main.hs:82,93), one thread per pixel of the tile, the whole
+// per-pixel path `li (cast u v)` (main.hs:73) inline: camera ray -> closest hit -> shade ->
+// shadow probes -> (reflection levels) -> pixel store at w*v+u (main.hs:100).
+// ---------------------------------------------------------------------------------------------
+template <bool ORDERED>
+__global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ RenderParams P) {
+  const int4 win = P.tiles[blockIdx.x];
+  const int th = win.w - win.y;
+  const int npx = (win.z - win.x) * th;
+  Counters cnt;
+  cnt.primary = cnt.shadow = cnt.secondary = 0;
+  for (int i = threadIdx.x; i < npx; i += blockDim.x) {
+    const int u = win.x + i / th, v = win.y + i % th;   // [(u, v) | u <- [x0..x1-1], v <- [y0..y1-1]]
+    const uint32_t pixel = (uint32_t)(P.width * v + u);
+    V3 acc = mk(0.0f, 0.0f, 0.0f), L = acc;
+    uint32_t prim0 = kNoHit;
+    for (int s = 0; s < P.spp; ++s) {
+      const float fu = (float)u + sampleOffset(P.seed, pixel, (uint32_t)s, 0);
+      const float fv = (float)v + sampleOffset(P.seed, pixel, (uint32_t)s, 1);
+      const Ray ray = cameraRay(P, fu, fv);
+      cnt.primary++;
+      uint32_t prim;
+      L = radiance<ORDERED>(P, ray, cnt, prim);
+      if (s == 0) prim0 = prim;
+      acc = vadd(acc, L);
+    }
+    if (P.spp != 1) {
+      const float n = (float)P.spp;
+      L = mk(__fdiv_rn(acc.x, n), __fdiv_rn(acc.y, n), __fdiv_rn(acc.z, n));
+    }
+    float* out = P.rgb + 3 * (size_t)pixel;
+    out[0] = L.x; out[1] = L.y; out[2] = L.z;
+    if (P.primid) P.primid[pixel] = prim0;
+  }
+  // ray counters: one atomic per warp per counter
+  const unsigned full = 0xFFFFFFFFu;
+  const uint32_t p = __reduce_add_sync(full, cnt.primary);
+  const uint32_t sh = __reduce_add_sync(full, cnt.shadow);
+  const uint32_t se = __reduce_add_sync(full, cnt.secondary);
+  if ((threadIdx.x & 31) == 0) {
+    if (p) atomicAdd(&P.counters[0], (unsigned long long)p);
+    if (sh) atomicAdd(&P.counters[1], (unsigned long long)sh);
+    if (se) atomicAdd(&P.counters[2], (unsigned long long)se);
+  }
+}
+
+cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_t* launches) {
+  if (P.nTiles == 0) return cudaSuccess;
+  if (P.traversal == 1) k_render_mega<true><<<P.nTiles, 256, 0, stream>>>(P);
+  else k_render_mega<false><<<P.nTiles, 256, 0, stream>>>(P);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace yb

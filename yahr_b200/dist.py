@@ -1,0 +1,151 @@
+"""One-process-per-GPU tile-sharded rendering.
+
+Every rank holds a replica of the (read-only) scene and renders the reference's own tile windows
+strided over ranks (tile i -> rank i mod G, Sampling.hs:9-21).  The frame ends up on rank 0.
+The only exchange is at the end of a frame -- the reference's `concat` of per-tile sample lists
+(main.hs:83,95) -- and there are two ways to do it:
+
+  "p2p"    (default on CUDA) rank 0's frame buffer is mapped into every rank through CUDA IPC and
+           the render kernel stores each finished pixel straight into it over NVLink: the gather
+           is fused into the kernel's epilogue and overlaps traversal.  A one-element NCCL
+           all-reduce on the render stream is the completion fence.
+  "reduce" every rank renders into a zeroed local full frame and the frames are summed onto rank 0
+           with one NCCL reduce -- exact, because every pixel has exactly one owner and x + 0 = x.
+           This is the plain-library baseline.
+
+torch / torch.distributed are plumbing (device memory, streams, process group); all rendering goes
+through the C ABI of libyahr_b200.so.
+"""
+import numpy as np
+
+from . import api
+
+
+class TileShardedRenderer:
+    def __init__(self, scene, cam, mode="p2p", want_primid=False, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.group = group
+        self.cam = cam
+        self.width, self.height = api.image_size(cam)
+        self.mode = mode if self.world > 1 else "local"
+        self.scene = api.Scene(scene)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = (self.height, self.width, 3)
+        self.want_primid = want_primid
+        self.frame = None         # rank 0 (and every rank in "reduce" mode): the frame tensor
+        self.primid = None
+        self._peer_rgb = None     # "p2p": rank 0's frame as seen from this rank
+        self._peer_pid = None
+        self._fence = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self.mode in ("local", "reduce") or self.rank == 0:
+            self.frame = torch.zeros(shape, dtype=torch.float32, device=dev)
+            if want_primid:
+                self.primid = torch.zeros((self.height, self.width), dtype=torch.int32, device=dev)
+        if self.mode == "p2p":
+            handles = [None]
+            if self.rank == 0:
+                L = api.lib()
+                import ctypes as C
+                hb = C.create_string_buffer(64)
+                api._check(L.yahr_b200_ipc_export(C.c_void_p(self.frame.data_ptr()), hb))
+                hp = None
+                if want_primid:
+                    hp_b = C.create_string_buffer(64)
+                    api._check(L.yahr_b200_ipc_export(C.c_void_p(self.primid.data_ptr()), hp_b))
+                    hp = hp_b.raw
+                # torch's caching allocator sub-allocates: ship the offset inside the IPC block too
+                handles = [(hb.raw, hp, self._alloc_offset(self.frame), self._alloc_offset(self.primid))]
+            dist.broadcast_object_list(handles, src=0, group=group)
+            if self.rank != 0:
+                import ctypes as C
+                L = api.lib()
+                hb, hp, off_rgb, off_pid = handles[0]
+                p = C.c_void_p()
+                api._check(L.yahr_b200_ipc_open(hb, C.byref(p)))
+                self._peer_base_rgb = p.value
+                self._peer_rgb = p.value + off_rgb
+                if hp is not None:
+                    q = C.c_void_p()
+                    if hp == hb:
+                        q = p
+                    else:
+                        api._check(L.yahr_b200_ipc_open(hp, C.byref(q)))
+                    self._peer_pid = q.value + off_pid
+            dist.barrier(group=group)
+
+    def _alloc_offset(self, t):
+        """Offset of a tensor inside its cudaMalloc block (cudaIpcGetMemHandle refers to the block)."""
+        if t is None:
+            return 0
+        import ctypes as C
+        cudart = self.torch.cuda.cudart()
+        # cuMemGetAddressRange through the runtime is not exposed; use the driver API via ctypes
+        drv = C.CDLL("libcuda.so.1")
+        base = C.c_uint64()
+        size = C.c_size_t()
+        rc = drv.cuMemGetAddressRange_v2(C.byref(base), C.byref(size), C.c_uint64(t.data_ptr()))
+        if rc != 0:
+            raise RuntimeError("cuMemGetAddressRange failed: %d" % rc)
+        del cudart
+        return t.data_ptr() - base.value
+
+    def render(self, recursion_depth=1, spp=1, seed=0, traversal=api.TRAVERSAL_REFERENCE, kernel=0):
+        """Enqueue one frame on the current stream; the frame is complete on rank 0 once the
+        stream has drained.  Returns nothing (no host sync)."""
+        torch, dist = self.torch, self.dist
+        stream = torch.cuda.current_stream().cuda_stream
+        kw = dict(recursion_depth=recursion_depth, spp=spp, seed=seed, traversal=traversal, stream=stream,
+                  stats=False, kernel=kernel)
+        if self.mode == "local":
+            self.scene.render_device(self.cam, self.frame.data_ptr(),
+                                     self.primid.data_ptr() if self.primid is not None else None, **kw)
+            return
+        kw.update(tile_stride=self.world, tile_offset=self.rank)
+        if self.mode == "p2p":
+            if self.rank == 0:
+                rgb, pid = self.frame.data_ptr(), (self.primid.data_ptr() if self.primid is not None else None)
+            else:
+                rgb, pid = self._peer_rgb, self._peer_pid
+            self.scene.render_device(self.cam, rgb, pid, **kw)
+            dist.all_reduce(self._fence, group=self.group)      # completion fence on the render stream
+        elif self.mode == "reduce":
+            self.frame.zero_()
+            self.scene.render_device(self.cam, self.frame.data_ptr(), None, **kw)
+            dist.reduce(self.frame, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+            if self.primid is not None:
+                self.primid.zero_()
+                self.scene.render_device(self.cam, self.frame.data_ptr(), self.primid.data_ptr(), **kw)
+                dist.reduce(self.primid, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            raise ValueError("unknown mode " + self.mode)
+
+    def stats_render(self, **kw):
+        """One synchronous local render of this rank's tiles into a scratch frame, returning the
+        library's stats (ray counts, kernel ms)."""
+        torch = self.torch
+        scratch = torch.empty((self.height, self.width, 3), dtype=torch.float32, device="cuda")
+        st = self.scene.render_device(self.cam, scratch.data_ptr(), None, tile_stride=self.world,
+                                      tile_offset=self.rank, stream=torch.cuda.current_stream().cuda_stream, **kw)
+        return st
+
+    def close(self):
+        if self._peer_rgb is not None:
+            import ctypes as C
+            api.lib().yahr_b200_ipc_close(C.c_void_p(self._peer_base_rgb))
+            self._peer_rgb = None
+        self.scene.close()
+
+
+def gather_tiles_reference(width, height, world_size, per_rank_frames):
+    """Host-side statement of what the exchange must produce (used by the gloo CPU tests):
+    pixel (u, v) comes from the rank that owns its tile."""
+    from . import tiles
+    out = np.zeros_like(per_rank_frames[0])
+    wins = tiles.tile_windows(width, height)
+    for i, (x0, y0, x1, y1) in enumerate(wins):
+        out[y0:y1, x0:x1] = per_rank_frames[i % world_size][y0:y1, x0:x1]
+    return out

@@ -1,0 +1,25 @@
+"""The reference's tile arithmetic (Sampling.hs:5-21, main.hs:109-131) as used for sharding.
+
+The data-parallel unit of the reference is one `squareBatches` window per spark / Par task
+(main.hs:82,93).  The multi-GPU driver assigns those same windows to ranks, strided:
+tile i -> rank i mod G.  The arithmetic itself lives in the C library
+(yahr_b200_num_batches / yahr_b200_batch_window); this module only enumerates.
+"""
+from . import api
+
+
+def tile_windows(width, height, num_threads=1):
+    """All windows (x0, y0, x1, y1) of squareBatches width height nBatches, in batch order."""
+    n = api.num_batches(num_threads, width, height)
+    return [api.batch_window(width, height, i, n) for i in range(n)]
+
+
+def rank_tiles(width, height, world_size, rank, num_threads=1):
+    """Indices of the tiles rank `rank` of `world_size` renders."""
+    n = api.num_batches(num_threads, width, height)
+    return list(range(rank, n, world_size))
+
+
+def rank_pixel_count(width, height, world_size, rank):
+    wins = tile_windows(width, height)
+    return sum((x1 - x0) * (y1 - y0) for (x0, y0, x1, y1) in wins[rank::world_size])
