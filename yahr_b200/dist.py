@@ -114,11 +114,12 @@ class TileShardedRenderer:
             dist.all_reduce(self._fence, group=self.group)      # completion fence on the render stream
         elif self.mode == "reduce":
             self.frame.zero_()
-            self.scene.render_device(self.cam, self.frame.data_ptr(), None, **kw)
-            dist.reduce(self.frame, dst=0, op=dist.ReduceOp.SUM, group=self.group)
             if self.primid is not None:
                 self.primid.zero_()
-                self.scene.render_device(self.cam, self.frame.data_ptr(), self.primid.data_ptr(), **kw)
+            self.scene.render_device(self.cam, self.frame.data_ptr(),
+                                     self.primid.data_ptr() if self.primid is not None else None, **kw)
+            dist.reduce(self.frame, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+            if self.primid is not None:
                 dist.reduce(self.primid, dst=0, op=dist.ReduceOp.SUM, group=self.group)
         else:
             raise ValueError("unknown mode " + self.mode)
