@@ -40,7 +40,10 @@ def _load_bytes_per_ray():
         return {}
 
 
-BYTES_PER_RAY = _load_bytes_per_ray()   # committed output of tools/count_bytes_per_ray.py
+BYTES_PER_RAY = _load_bytes_per_ray()
+# dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed `ncu --set full` captures
+# (profiles/*_ncu_full_*.txt); None where no capture exists.
+TRAFFIC_BYTES = {("c4-terrain", "mega"): 98.76e6 + 58.22e6}   # committed output of tools/count_bytes_per_ray.py
 
 
 def workload(name):
@@ -232,7 +235,7 @@ def run_ours(args):
         R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
+    kernel_ms, phase_ms = [], []
     with ClockSampler(local) as clk:
         barrier()
         for i in range(args.steps):
@@ -248,6 +251,7 @@ def run_ours(args):
             flush.zero_()
             stk = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
             kernel_ms.append(stk["gpu_ms"])
+            phase_ms.append(stk["phase_ms"])
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)       # max over ranks, per step
@@ -301,9 +305,15 @@ def run_ours(args):
     roofline = None
     if k_ms and bpr:
         achieved = rays_local * bpr / (k_ms * 1e-3) / 1e9
+        wf = launches_per_step > 1
+        ph = [float(x) for x in np.mean(np.asarray(phase_ms), axis=0)]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "k_render_mega", "kernel_ms": k_ms, "bytes_per_ray": bpr,
-                    "rays_per_launch": rays_local, "peak_source": peak_src,
+                    "traffic": TRAFFIC_BYTES.get((args.workload, "wavefront" if wf else "mega")),
+                    "kernel": ("k_wf_primary + k_wf_shade + k_wf_shadow (one frame = one launch of each; "
+                               "k_wf_primary dominant)") if wf else "k_render_mega",
+                    "kernel_ms": k_ms,
+                    "phase_ms": {"primary_trace": ph[0], "shade": ph[1], "shadow_trace": ph[2]} if wf else None,
+                    "bytes_per_ray": bpr, "rays_per_launch": rays_local, "peak_source": peak_src,
                     "note": "algorithmic bytes under the reference's traversal; traversal is latency/divergence "
                             "bound, see DESIGN.md"}
 

@@ -119,6 +119,8 @@ typedef struct yahr_stats {
   uint64_t h2d_bytes, d2h_bytes;
   uint32_t launches;        /* kernel launches issued by this call */
   uint32_t tiles;           /* reference tiles rendered by this call */
+  double phase_ms[4];       /* wavefront set: primary trace, shade, shadow trace (first sample pass);
+                               megakernel: [0] = the kernel */
 } yahr_stats;
 
 typedef struct yahr_scene_info {

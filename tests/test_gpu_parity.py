@@ -46,12 +46,18 @@ def gpu_render_modes(sc, cam, depth=1, spp=1, seed=0):
     rgb, pid, st = s.render(cam, recursion_depth=depth, spp=spp, seed=seed)
     w, h = api.image_size(cam)
     outs = {"host": (rgb, pid, st)}
-    for name, mode in (("reference", api.TRAVERSAL_REFERENCE), ("ordered", api.TRAVERSAL_ORDERED)):
-        d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
-        d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
-        st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
-                              traversal=mode, stream=torch.cuda.current_stream().cuda_stream)
-        outs[name] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
+    # kernel 1 = megakernel, 2 = persistent wavefront set (recursion depth 1 only)
+    kernels = (("mega", 1), ("wavefront", 2)) if depth == 1 else (("mega", 1),)
+    for kname, kernel in kernels:
+        for name, mode in (("reference", api.TRAVERSAL_REFERENCE), ("ordered", api.TRAVERSAL_ORDERED)):
+            d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
+            d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
+            st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp,
+                                  seed=seed, traversal=mode, stream=torch.cuda.current_stream().cuda_stream,
+                                  kernel=kernel)
+            outs[kname + "/" + name] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
+    outs["reference"] = outs["mega/reference"]
+    outs["ordered"] = outs["mega/ordered"]
     s.close()
     return outs
 
@@ -86,17 +92,23 @@ def test_parity_small_scenes(name):
     orgb, opid, _, ost = o.render(cam)
     o.close()
     outs = gpu_render_modes(sc, cam)
-    for mode in ("host", "reference"):
+    for mode in ("host", "mega/reference", "wavefront/reference"):
         rgb, pid, st = outs[mode]
         compare(rgb, pid, orgb, opid, 1.0, "%s/%s" % (name, mode))
         assert st["n_primary"] == ost["n_primary"]
         assert st["n_shadow"] == ost["n_shadow"], "shadow-ray count differs from Integrators.hs:59 semantics"
         assert st["launches"] >= 1
-    rgb, pid, st = outs["ordered"]
-    compare(rgb, pid, orgb, opid, 0.9999, name + "/ordered")
-    # host and device entries are the same computation
-    assert np.array_equal(outs["host"][1], outs["reference"][1])
-    assert np.array_equal(outs["host"][0].view(np.uint32), outs["reference"][0].view(np.uint32))
+    for mode in ("mega/ordered", "wavefront/ordered"):
+        rgb, pid, st = outs[mode]
+        compare(rgb, pid, orgb, opid, 0.9999, name + "/" + mode)
+    # the host entry (default kernel set) and the device entry are the same computation, and the two
+    # kernel sets agree bit for bit on IDs (radiance: same arithmetic, so bit-equal as well)
+    assert np.array_equal(outs["host"][1], outs["wavefront/reference"][1])
+    assert np.array_equal(outs["mega/reference"][1], outs["wavefront/reference"][1])
+    a, b = outs["mega/reference"][0], outs["wavefront/reference"][0]
+    nan = np.isnan(a) | np.isnan(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(np.where(nan, 0, a), np.where(nan, 0, b))
 
 
 @pytest.mark.parametrize("depth", [0, 2, 3])
@@ -121,10 +133,11 @@ def test_parity_spp_extension():
     o1rgb, o1pid, _, _ = o.render(cam, spp=1)
     o.close()
     outs = gpu_render_modes(sc, cam, spp=4, seed=0x1234ABCD5678)
-    rgb, pid, st = outs["reference"]
-    compare(rgb, pid, orgb, opid, 1.0, "bunny spp4")
-    assert np.array_equal(pid, o1pid)          # primitive ID is sample 0's
-    assert st["n_primary"] == 4 * 160 * 90
+    for mode in ("mega/reference", "wavefront/reference", "host"):
+        rgb, pid, st = outs[mode]
+        compare(rgb, pid, orgb, opid, 1.0, "bunny spp4 " + mode)
+        assert np.array_equal(pid, o1pid)          # primitive ID is sample 0's
+        assert st["n_primary"] == 4 * 160 * 90
 
 
 def test_tile_sharding_partitions_the_image():

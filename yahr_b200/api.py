@@ -56,10 +56,13 @@ class RenderOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_primary", C.c_uint64), ("n_shadow", C.c_uint64), ("n_secondary", C.c_uint64),
                 ("gpu_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("tiles", C.c_uint32)]
+                ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("tiles", C.c_uint32),
+                ("phase_ms", C.c_double * 4)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["phase_ms"] = list(self.phase_ms)
+        return d
 
 
 class SceneInfo(C.Structure):

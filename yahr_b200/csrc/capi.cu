@@ -58,7 +58,7 @@ T* devUpload(const std::vector<T>& v, uint64_t& bytes) {
   return p;
 }
 
-struct TileSet { int4* d_tiles = nullptr; uint32_t n = 0; };
+struct TileSet { int4* d_tiles = nullptr; uint32_t* d_tileStart = nullptr; uint32_t n = 0; uint32_t nItems = 0; };
 
 }  // namespace
 
@@ -75,18 +75,28 @@ struct yahr_scene {
   yahr_scene_info info{};
   // per (width, height, stride, offset) tile lists, uploaded once
   std::map<std::tuple<int, int, int, int>, TileSet> tiles;
+  // wavefront scratch (grown on demand): hit records, shadow queue, work counters, spp buffers
+  float* wfHitT = nullptr; uint32_t* wfHitIdx = nullptr; size_t wfItems = 0;
+  float4 *wfQ0 = nullptr, *wfQ1 = nullptr, *wfQ2 = nullptr; unsigned char* wfVis = nullptr; size_t wfEntries = 0;
+  uint32_t* wfWork = nullptr;
+  float *wfSampleBuf = nullptr, *wfAccum = nullptr; size_t wfPixels = 0;
+  int numSMs = 148;
   // frame buffers of the host-buffer entry (grown on demand)
   float* d_rgb = nullptr;
   uint32_t* d_primid = nullptr;
   size_t framePixels = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid);
-    for (auto& kv : tiles) cudaFree(kv.second.d_tiles);
+    for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
+    cudaFree(wfHitT); cudaFree(wfHitIdx); cudaFree(wfQ0); cudaFree(wfQ1); cudaFree(wfQ2); cudaFree(wfVis);
+    cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (auto e : phaseEv) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -105,14 +115,20 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
   // image does not depend on them).
   const int64_t nBatches = numBatches(1, w, h);
   std::vector<int4> host;
+  std::vector<uint32_t> start(1, 0u);
   for (int64_t b = offset; b < nBatches; b += stride) {
     TileWindow t = batchWindow(w, h, b, nBatches);
-    if (t.x1 > t.x0 && t.y1 > t.y0) host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
+    if (t.x1 > t.x0 && t.y1 > t.y0) {
+      host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
+      start.push_back(start.back() + (uint32_t)((t.x1 - t.x0) * (t.y1 - t.y0)));
+    }
   }
   TileSet ts;
   ts.n = (uint32_t)host.size();
+  ts.nItems = start.back();
   uint64_t bytes = 0;
   ts.d_tiles = devUpload(host, bytes);
+  ts.d_tileStart = devUpload(start, bytes);
   return sc->tiles.emplace(key, ts).first->second;
 }
 
@@ -147,8 +163,47 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
 
   uint32_t launches = 0;
   CU(cudaMemsetAsync(sc->d_counters, 0, 3 * sizeof(unsigned long long), stream));
+  // kernel selection: 0 = default (wavefront set for direct lighting, megakernel for recursion
+  // depth != 1), 1 = megakernel, 2 = wavefront
+  const bool wavefront = opts->kernel == 2 || (opts->kernel == 0 && opts->recursion_depth == 1);
+  if (opts->kernel == 2 && opts->recursion_depth != 1)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
+  WavefrontParams W{};
+  if (wavefront) {
+    const uint32_t nL = sc->dev.nLights;
+    const size_t items = ts.nItems, entries = (size_t)ts.nItems * (nL > 1 ? nL : 1);
+    if (items > sc->wfItems) {
+      cudaFree(sc->wfHitT); cudaFree(sc->wfHitIdx); sc->wfHitT = nullptr; sc->wfHitIdx = nullptr; sc->wfItems = 0;
+      CU(cudaMalloc(&sc->wfHitT, items * sizeof(float)));
+      CU(cudaMalloc(&sc->wfHitIdx, items * sizeof(uint32_t)));
+      sc->wfItems = items;
+    }
+    if (entries > sc->wfEntries) {
+      cudaFree(sc->wfQ0); cudaFree(sc->wfQ1); cudaFree(sc->wfQ2); cudaFree(sc->wfVis);
+      sc->wfQ0 = sc->wfQ1 = sc->wfQ2 = nullptr; sc->wfVis = nullptr; sc->wfEntries = 0;
+      CU(cudaMalloc(&sc->wfQ0, entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfQ1, entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfQ2, entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfVis, entries));
+      sc->wfEntries = entries;
+    }
+    const size_t px = (size_t)cs.width * cs.height;
+    if (opts->spp > 1 && px > sc->wfPixels) {
+      cudaFree(sc->wfSampleBuf); cudaFree(sc->wfAccum); sc->wfSampleBuf = sc->wfAccum = nullptr; sc->wfPixels = 0;
+      CU(cudaMalloc(&sc->wfSampleBuf, px * 3 * sizeof(float)));
+      CU(cudaMalloc(&sc->wfAccum, px * 3 * sizeof(float)));
+      sc->wfPixels = px;
+    }
+    if (!sc->wfWork) CU(cudaMalloc(&sc->wfWork, 8 * sizeof(uint32_t)));
+    W.base = P;
+    W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
+    W.hitT = sc->wfHitT; W.hitIdx = sc->wfHitIdx;
+    W.q0 = sc->wfQ0; W.q1 = sc->wfQ1; W.q2 = sc->wfQ2; W.visibility = nL > 1 ? sc->wfVis : nullptr;
+    W.work = sc->wfWork; W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
+  }
   if (stats) CU(cudaEventRecord(sc->ev0, stream));
-  CU(launchRenderMega(P, stream, &launches));
+  if (wavefront) CU(launchWavefront(W, sc->numSMs, stream, &launches, stats ? sc->phaseEv : nullptr));
+  else CU(launchRenderMega(P, stream, &launches));
   if (stats) CU(cudaEventRecord(sc->ev1, stream));
   if (stats) {
     unsigned long long c[3];
@@ -159,6 +214,15 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
     std::memset(stats, 0, sizeof(*stats));
     stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
     stats->gpu_ms = ms;
+    if (wavefront) {
+      for (int k = 0; k < 3; ++k) {
+        float pm = 0;
+        CU(cudaEventElapsedTime(&pm, sc->phaseEv[k], sc->phaseEv[k + 1]));
+        stats->phase_ms[k] = pm;
+      }
+    } else {
+      stats->phase_ms[0] = ms;
+    }
     stats->launches = launches;
     stats->tiles = ts.n;
     stats->wall_ms = nowMs() - w0;
@@ -242,6 +306,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
 
     sc = new yahr_scene();
     CU(cudaGetDevice(&sc->device));
+    CU(cudaDeviceGetAttribute(&sc->numSMs, cudaDevAttrMultiProcessorCount, sc->device));
     const double t2 = nowMs();
     uint64_t bytes = 0;
     static_assert(sizeof(FlatNode) == 4 * sizeof(float4), "node layout");
@@ -258,6 +323,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     CU(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaEventCreate(&sc->ev0));
     CU(cudaEventCreate(&sc->ev1));
+    for (auto& e : sc->phaseEv) CU(cudaEventCreate(&e));
     CU(cudaDeviceSynchronize());
     const double t3 = nowMs();
 

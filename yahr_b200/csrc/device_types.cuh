@@ -50,4 +50,24 @@ struct RenderParams {
   unsigned long long* counters;  // [0] primary, [1] shadow, [2] secondary
 };
 
+// Parameter block of the wavefront kernel set (wavefront.cu).  "item" = one pixel of this call's
+// tiles, numbered tile-major (tile order, then u-major inside the tile, Sampling.hs:6).
+struct WavefrontParams {
+  RenderParams base;
+  const uint32_t* tileStart;  // nTiles + 1 prefix sums of the tile pixel counts
+  uint32_t nItems;
+  uint32_t sample;            // sample index of this pass (spp > 1 runs one pass per sample)
+  uint32_t dense;             // several lights: shadow slots entry = item * nLights + light
+  float* hitT;                // per item: t of the closest hit
+  uint32_t* hitIdx;           // per item: DFS position of the closest hit (0xFFFFFFFF = miss)
+  float4* q0;                 // shadow probes: (origin.xyz, tMax)
+  float4* q1;                 //                (direction.xyz, pixel index bits)
+  float4* q2;                 //                (contribution.rgb, -)
+  unsigned char* visibility;  // dense mode: per slot 1 = unoccluded
+  uint32_t* work;             // [0] primary work counter, [1] shadow work counter, [2] queue length, [3] probes
+  float* sampleOut;           // where this pass writes its radiance (the frame, or sampleBuf for spp > 1)
+  float* sampleBuf;           // W*H*3 scratch (spp > 1)
+  float* accum;               // W*H*3 running sum (spp > 1)
+};
+
 }  // namespace yb

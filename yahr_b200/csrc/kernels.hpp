@@ -8,3 +8,10 @@ namespace yb {
 cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_t* launches);
 
 }  // namespace yb
+
+namespace yb {
+// Persistent-thread wavefront kernel set (primary trace, shade, shadow trace, resolve); depth 1 only.
+// phaseEvents: NULL or 4 events recorded before primary / shade / shadow and after shadow (first sample).
+cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
+                            cudaEvent_t* phaseEvents);
+}  // namespace yb
