@@ -222,7 +222,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ray counts and kernel-only time of this rank's share (library stats, synchronous)
-    st = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+    st = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
     rays_local = st["n_primary"] + st["n_shadow"] + st["n_secondary"]
     rays_t = torch.tensor([rays_local, st["n_primary"], st["n_shadow"]], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -232,7 +232,7 @@ def run_ours(args):
 
     # ---- value: device-resident ------------------------------------------------------------
     for _ in range(args.warmup):
-        R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+        R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms, phase_ms = [], []
@@ -243,13 +243,13 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
             ev[i][0].record()
-            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             ev[i][1].record()
         barrier()
         # kernel-only time of the dominant kernel, measured live with CUDA events (library stats)
         for i in range(min(args.steps, 5)):
             flush.zero_()
-            stk = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            stk = R.stats_render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             kernel_ms.append(stk["gpu_ms"])
             phase_ms.append(stk["phase_ms"])
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
@@ -284,7 +284,7 @@ def run_ours(args):
             flush.zero_()
             barrier()
             t = time.perf_counter()
-            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel)
+            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             if rank == 0:
                 host_rgb.copy_(R.frame, non_blocking=True)
             barrier()
@@ -352,6 +352,7 @@ def main():
     ap.add_argument("--depth", type=int, default=1)
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--tune", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

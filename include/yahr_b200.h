@@ -160,6 +160,11 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
 int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
                             float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats);
 
+/* Pinned host memory for output buffers (optional): device-to-host copies into it run at full PCIe
+ * speed and overlap with rendering inside yahr_b200_render.  Any host pointer works as an output. */
+int yahr_b200_host_alloc(size_t bytes, void** out);
+int yahr_b200_host_free(void* p);
+
 /* --- tile arithmetic of the reference (Sampling.hs:9-21, main.hs:109-110, 128-131) ------------- */
 int64_t yahr_b200_num_batches(int64_t num_threads, int64_t width, int64_t height);
 int yahr_b200_batch_window(int64_t width, int64_t height, int64_t num, int64_t count, int32_t out_x0y0x1y1[4]);

@@ -256,13 +256,14 @@ class Scene:
 
     def render_device(self, cam, d_rgb, d_primid=None, recursion_depth=1, spp=1, seed=0,
                       traversal=TRAVERSAL_REFERENCE, tile_stride=1, tile_offset=0, stream=None, stats=True,
-                      kernel=0):
+                      kernel=0, tune=0):
         """Device-buffer entry (yahr_b200_render_device).  d_rgb / d_primid are raw device pointers
         (ints), e.g. torch_tensor.data_ptr().  Returns a stats dict (synchronises) or None."""
         c = make_camera(cam)
         o = RenderOpts()
         o.recursion_depth, o.spp, o.seed = recursion_depth, spp, seed
         o.traversal, o.tile_stride, o.tile_offset, o.kernel = traversal, tile_stride, tile_offset, kernel
+        o.reserved[0] = tune
         st = Stats() if stats else None
         _check(lib().yahr_b200_render_device(self._h, C.byref(c), C.byref(o), C.c_void_p(d_rgb),
                                              C.c_void_p(d_primid) if d_primid else None,

@@ -154,10 +154,6 @@ class Builder {
     return id;
   }
 
-  static void putBox(float* dst, const Box& b) {
-    dst[0] = b.lo.x; dst[1] = b.lo.y; dst[2] = b.lo.z; dst[3] = b.hi.x; dst[4] = b.hi.y; dst[5] = b.hi.z;
-  }
-
   void flatten() {
     const size_t n = out_.nodes.size();
     std::vector<uint32_t> innerIndex(n, 0);
@@ -186,8 +182,11 @@ class Builder {
       const RefNode& nd = out_.nodes[i];
       if (nd.kind != kInner) continue;
       FlatNode& f = out_.flat[innerIndex[i]];
-      putBox(f.lbox, out_.nodes[nd.left].box);
-      putBox(f.rbox, out_.nodes[nd.right].box);
+      const Box& lb = out_.nodes[nd.left].box;
+      const Box& rb = out_.nodes[nd.right].box;
+      f.lxy[0] = lb.lo.x; f.lxy[1] = lb.lo.y; f.lxy[2] = lb.hi.x; f.lxy[3] = lb.hi.y;
+      f.rxy[0] = rb.lo.x; f.rxy[1] = rb.lo.y; f.rxy[2] = rb.hi.x; f.rxy[3] = rb.hi.y;
+      f.z[0] = lb.lo.z; f.z[1] = lb.hi.z; f.z[2] = rb.lo.z; f.z[3] = rb.hi.z;
       f.left = refOf(nd.left);
       f.right = refOf(nd.right);
       f.pad0 = f.pad1 = 0;

@@ -30,9 +30,10 @@ static const uint32_t kRefNull = 0xFFFFFFFFu;
 static const uint32_t kRefLeafBit = 0x80000000u;   // single-primitive leaf: kRefLeafBit | dfs position
 static const uint32_t kRefMultiBits = 0xC0000000u; // multi-leaf: kRefMultiBits | index into multiLeaves
 
-struct FlatNode {          // 64 bytes = 4 x float4
-  float lbox[6];           // left child box  lo.xyz hi.xyz
-  float rbox[6];           // right child box
+struct FlatNode {          // 64 bytes = 4 x float4, components paired for packed f32x2 slab math
+  float lxy[4];            // left child:  lo.x lo.y hi.x hi.y
+  float rxy[4];            // right child: lo.x lo.y hi.x hi.y
+  float z[4];              // left lo.z, left hi.z, right lo.z, right hi.z
   uint32_t left, right;    // child references
   uint32_t pad0, pad1;
 };

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libyahr_b200.so (include/yahr_b200.h).  No CPU fallback: every compute
 // entry point needs a CUDA device and fails with YAHR_ERR_NO_DEVICE / YAHR_ERR_CUDA otherwise.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -58,7 +59,14 @@ T* devUpload(const std::vector<T>& v, uint64_t& bytes) {
   return p;
 }
 
-struct TileSet { int4* d_tiles = nullptr; uint32_t* d_tileStart = nullptr; uint32_t n = 0; uint32_t nItems = 0; };
+struct TileSet {
+  int4* d_tiles = nullptr;
+  uint32_t* d_tileStart = nullptr;
+  uint32_t n = 0, nItems = 0;
+  std::vector<int4> hostTiles;        // windows, batch order (row-major over the tile grid)
+  std::vector<uint32_t> hostStart;    // n + 1 prefix sums of the tile pixel counts
+  uint32_t gridNx = 0;                // tiles per tile-row when the set is the whole image (stride 1)
+};
 
 }  // namespace
 
@@ -76,7 +84,6 @@ struct yahr_scene {
   // per (width, height, stride, offset) tile lists, uploaded once
   std::map<std::tuple<int, int, int, int>, TileSet> tiles;
   // wavefront scratch (grown on demand): hit records, shadow queue, work counters, spp buffers
-  float* wfHitT = nullptr; uint32_t* wfHitIdx = nullptr; size_t wfItems = 0;
   float4 *wfQ0 = nullptr, *wfQ1 = nullptr, *wfQ2 = nullptr; unsigned char* wfVis = nullptr; size_t wfEntries = 0;
   uint32_t* wfWork = nullptr;
   float *wfSampleBuf = nullptr, *wfAccum = nullptr; size_t wfPixels = 0;
@@ -87,16 +94,21 @@ struct yahr_scene {
   size_t framePixels = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t renderStream = nullptr, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
+  std::vector<cudaEvent_t> bandEvents;
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
-    cudaFree(wfHitT); cudaFree(wfHitIdx); cudaFree(wfQ0); cudaFree(wfQ1); cudaFree(wfQ2); cudaFree(wfVis);
+    cudaFree(wfQ0); cudaFree(wfQ1); cudaFree(wfQ2); cudaFree(wfVis);
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto e : phaseEv) if (e) cudaEventDestroy(e);
+    for (auto e : bandEvents) cudaEventDestroy(e);
+    if (renderStream) cudaStreamDestroy(renderStream);
+    if (copyStream) cudaStreamDestroy(copyStream);
   }
 };
 
@@ -126,15 +138,31 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
   TileSet ts;
   ts.n = (uint32_t)host.size();
   ts.nItems = start.back();
+  ts.hostTiles = host;
+  ts.hostStart = start;
+  if (stride == 1) {                                   // (nx, ny) = loop count 1   (Sampling.hs:11-15)
+    int64_t nx = nBatches, ny = 1;
+    while (nx % 2 == 0 && 2 * (int64_t)w * ny < (int64_t)h * nx) { nx /= 2; ny *= 2; }
+    ts.gridNx = (ts.n == (uint32_t)nBatches) ? (uint32_t)nx : 0;   // 0 when empty windows were dropped
+  }
   uint64_t bytes = 0;
   ts.d_tiles = devUpload(host, bytes);
   ts.d_tileStart = devUpload(start, bytes);
   return sc->tiles.emplace(key, ts).first->second;
 }
 
-int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb,
-                 uint32_t* d_primid, cudaStream_t stream, yahr_stats* stats, bool sync) {
+// Everything a frame needs, validated once; tiles are then enqueued in one or several ranges.
+struct FramePlan {
   CameraSetup cs;
+  const TileSet* ts = nullptr;
+  RenderParams P{};
+  WavefrontParams W{};
+  bool wavefront = false;
+};
+
+int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb, uint32_t* d_primid,
+              FramePlan& plan) {
+  CameraSetup& cs = plan.cs;
   std::string err;
   int rc = setupCamera(cam, cs, err);
   if (rc) return fail(rc, err);
@@ -145,10 +173,15 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
     return fail(YAHR_ERR_INVALID_ARGUMENT, "tile_stride/tile_offset invalid");
   if (opts->traversal != YAHR_TRAVERSAL_REFERENCE && opts->traversal != YAHR_TRAVERSAL_ORDERED)
     return fail(YAHR_ERR_INVALID_ARGUMENT, "unknown traversal mode");
+  // kernel selection: 0 = default (wavefront set for direct lighting, megakernel for recursion
+  // depth != 1), 1 = megakernel, 2 = wavefront
+  plan.wavefront = opts->kernel == 2 || (opts->kernel == 0 && opts->recursion_depth == 1);
+  if (opts->kernel == 2 && opts->recursion_depth != 1)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
 
-  const double w0 = nowMs();
   const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset);
-  RenderParams P{};
+  plan.ts = &ts;
+  RenderParams& P = plan.P;
   P.sc = sc->dev;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 4; ++j) P.vtf[4 * i + j] = cs.vtf.m[i][j];
@@ -161,23 +194,10 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
   P.rgb = d_rgb; P.primid = d_primid;
   P.counters = sc->d_counters;
 
-  uint32_t launches = 0;
-  CU(cudaMemsetAsync(sc->d_counters, 0, 3 * sizeof(unsigned long long), stream));
-  // kernel selection: 0 = default (wavefront set for direct lighting, megakernel for recursion
-  // depth != 1), 1 = megakernel, 2 = wavefront
-  const bool wavefront = opts->kernel == 2 || (opts->kernel == 0 && opts->recursion_depth == 1);
-  if (opts->kernel == 2 && opts->recursion_depth != 1)
-    return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
-  WavefrontParams W{};
-  if (wavefront) {
+  if (plan.wavefront) {
+    WavefrontParams& W = plan.W;
     const uint32_t nL = sc->dev.nLights;
-    const size_t items = ts.nItems, entries = (size_t)ts.nItems * (nL > 1 ? nL : 1);
-    if (items > sc->wfItems) {
-      cudaFree(sc->wfHitT); cudaFree(sc->wfHitIdx); sc->wfHitT = nullptr; sc->wfHitIdx = nullptr; sc->wfItems = 0;
-      CU(cudaMalloc(&sc->wfHitT, items * sizeof(float)));
-      CU(cudaMalloc(&sc->wfHitIdx, items * sizeof(uint32_t)));
-      sc->wfItems = items;
-    }
+    const size_t entries = (size_t)ts.nItems * (nL > 1 ? nL : 1);
     if (entries > sc->wfEntries) {
       cudaFree(sc->wfQ0); cudaFree(sc->wfQ1); cudaFree(sc->wfQ2); cudaFree(sc->wfVis);
       sc->wfQ0 = sc->wfQ1 = sc->wfQ2 = nullptr; sc->wfVis = nullptr; sc->wfEntries = 0;
@@ -196,14 +216,49 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
     }
     if (!sc->wfWork) CU(cudaMalloc(&sc->wfWork, 8 * sizeof(uint32_t)));
     W.base = P;
-    W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
-    W.hitT = sc->wfHitT; W.hitIdx = sc->wfHitIdx;
+    W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
     W.q0 = sc->wfQ0; W.q1 = sc->wfQ1; W.q2 = sc->wfQ2; W.visibility = nL > 1 ? sc->wfVis : nullptr;
+    // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
+    const uint32_t tune = (uint32_t)opts->reserved[0];
+    W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 4u;
+    W.blocksPerSM = (tune >> 16) & 0xFF;
+    W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
+    W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
     W.work = sc->wfWork; W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
   }
+  return YAHR_OK;
+}
+
+// Enqueues the kernels for tiles [first, first + count) of the plan's tile set.
+void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_t count, cudaStream_t stream,
+                  uint32_t* launches, cudaEvent_t* phaseEv) {
+  if (count == 0) return;
+  const TileSet& ts = *plan.ts;
+  if (plan.wavefront) {
+    WavefrontParams W = plan.W;
+    W.base.tiles = ts.d_tiles + first; W.base.nTiles = count;
+    W.tileStart = ts.d_tileStart + first;
+    W.itemBase = ts.hostStart[first];
+    W.nItems = ts.hostStart[first + count] - ts.hostStart[first];
+    CU(launchWavefront(W, sc->numSMs, stream, launches, phaseEv));
+  } else {
+    RenderParams P = plan.P;
+    P.tiles = ts.d_tiles + first; P.nTiles = count;
+    CU(launchRenderMega(P, stream, launches));
+  }
+}
+
+int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb,
+                 uint32_t* d_primid, cudaStream_t stream, yahr_stats* stats, bool sync) {
+  const double w0 = nowMs();
+  FramePlan plan;
+  int rc = planFrame(sc, cam, opts, d_rgb, d_primid, plan);
+  if (rc) return rc;
+  const TileSet& ts = *plan.ts;
+  uint32_t launches = 0;
+  CU(cudaMemsetAsync(sc->d_counters, 0, 3 * sizeof(unsigned long long), stream));
   if (stats) CU(cudaEventRecord(sc->ev0, stream));
-  if (wavefront) CU(launchWavefront(W, sc->numSMs, stream, &launches, stats ? sc->phaseEv : nullptr));
-  else CU(launchRenderMega(P, stream, &launches));
+  enqueueTiles(sc, plan, 0, ts.n, stream, &launches, stats ? sc->phaseEv : nullptr);
   if (stats) CU(cudaEventRecord(sc->ev1, stream));
   if (stats) {
     unsigned long long c[3];
@@ -214,7 +269,7 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
     std::memset(stats, 0, sizeof(*stats));
     stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
     stats->gpu_ms = ms;
-    if (wavefront) {
+    if (plan.wavefront && ts.n) {
       for (int k = 0; k < 3; ++k) {
         float pm = 0;
         CU(cudaEventElapsedTime(&pm, sc->phaseEv[k], sc->phaseEv[k + 1]));
@@ -386,39 +441,123 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
   if (!scene || !cam || !rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
   try {
     const double w0 = nowMs();
-    CameraSetup cs;
-    std::string err;
-    int rc = setupCamera(cam, cs, err);
-    if (rc) return fail(rc, err);
-    const size_t px = (size_t)cs.width * cs.height;
-    if (px > scene->framePixels) {
-      cudaFree(scene->d_rgb); cudaFree(scene->d_primid);
-      scene->d_rgb = nullptr; scene->d_primid = nullptr; scene->framePixels = 0;
-      CU(cudaMalloc(&scene->d_rgb, px * 3 * sizeof(float)));
-      CU(cudaMalloc(&scene->d_primid, px * sizeof(uint32_t)));
-      scene->framePixels = px;
-    }
     yahr_render_opts o{};
     o.recursion_depth = recursion_depth; o.spp = spp; o.seed = seed;
     o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = 1; o.tile_offset = 0;
-    yahr_stats local{};
-    rc = renderCommon(scene, cam, &o, scene->d_rgb, primid_out ? scene->d_primid : nullptr, nullptr, &local, true);
-    if (rc) return rc;
-    CU(cudaMemcpy(rgb_out, scene->d_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    local.d2h_bytes = px * 3 * sizeof(float);
-    if (primid_out) {
-      CU(cudaMemcpy(primid_out, scene->d_primid, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-      local.d2h_bytes += px * sizeof(uint32_t);
+    {
+      CameraSetup cs;
+      std::string err;
+      int rc0 = setupCamera(cam, cs, err);
+      if (rc0) return fail(rc0, err);
+      const size_t px0 = (size_t)cs.width * cs.height;
+      if (px0 > scene->framePixels) {
+        cudaFree(scene->d_rgb); cudaFree(scene->d_primid);
+        scene->d_rgb = nullptr; scene->d_primid = nullptr; scene->framePixels = 0;
+        CU(cudaMalloc(&scene->d_rgb, px0 * 3 * sizeof(float)));
+        CU(cudaMalloc(&scene->d_primid, px0 * sizeof(uint32_t)));
+        scene->framePixels = px0;
+      }
     }
-    local.h2d_bytes = sizeof(RenderParams);
-    local.wall_ms = nowMs() - w0;
-    if (stats) *stats = local;
+    FramePlan plan;
+    int rc = planFrame(scene, cam, &o, scene->d_rgb, primid_out ? scene->d_primid : nullptr, plan);
+    if (rc) return rc;
+    const TileSet& ts = *plan.ts;
+    const int W_ = plan.cs.width, H_ = plan.cs.height;
+    if (!scene->renderStream) CU(cudaStreamCreateWithFlags(&scene->renderStream, cudaStreamNonBlocking));
+    if (!scene->copyStream) CU(cudaStreamCreateWithFlags(&scene->copyStream, cudaStreamNonBlocking));
+    cudaStream_t rs = scene->renderStream, cp = scene->copyStream;
+
+    // The frame is rendered in horizontal BANDS of whole tile rows (tiles are numbered row-major over
+    // the tile grid, Sampling.hs:16), and every finished band is copied to the caller's buffer on a
+    // second stream while the next band renders, so the device-to-host transfer overlaps traversal.
+    // spp > 1 accumulates per pixel across sample passes inside a band, which works the same way.
+    uint32_t nBands = 1;
+    const uint32_t tileRows = ts.gridNx ? ts.n / ts.gridNx : 0;
+    if (tileRows >= 2) {
+      const char* env = getenv("YAHR_B200_BANDS");
+      uint32_t want = env ? (uint32_t)atoi(env) : 8u;
+      if (want < 1) want = 1;
+      nBands = want < tileRows ? want : tileRows;
+    }
+    while (scene->bandEvents.size() < nBands) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      scene->bandEvents.push_back(e);
+    }
+    uint32_t launches = 0;
+    CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
+    CU(cudaEventRecord(scene->ev0, rs));
+    uint64_t d2h = 0;
+    for (uint32_t b = 0; b < nBands; ++b) {
+      uint32_t first = 0, count = ts.n;
+      int y0 = 0, y1 = H_;
+      if (nBands > 1) {
+        const uint32_t r0 = (uint32_t)((uint64_t)tileRows * b / nBands), r1 = (uint32_t)((uint64_t)tileRows * (b + 1) / nBands);
+        first = r0 * ts.gridNx; count = (r1 - r0) * ts.gridNx;
+        y0 = ts.hostTiles[first].y; y1 = ts.hostTiles[first + count - 1].w;
+      }
+      enqueueTiles(scene, plan, first, count, rs, &launches, (b == 0) ? scene->phaseEv : nullptr);
+      CU(cudaEventRecord(scene->bandEvents[b], rs));
+      CU(cudaStreamWaitEvent(cp, scene->bandEvents[b], 0));
+      const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
+      CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
+                         (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+      d2h += (uint64_t)(y1 - y0) * rowBytes;
+      if (primid_out) {
+        const size_t idBytes = (size_t)W_ * sizeof(uint32_t);
+        CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
+                           (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
+        d2h += (uint64_t)(y1 - y0) * idBytes;
+      }
+    }
+    CU(cudaEventRecord(scene->ev1, rs));
+    unsigned long long c[3];
+    CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
+    CU(cudaStreamSynchronize(rs));
+    CU(cudaStreamSynchronize(cp));
+    if (stats) {
+      std::memset(stats, 0, sizeof(*stats));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+      stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
+      stats->gpu_ms = ms;
+      if (plan.wavefront && ts.n) {
+        for (int k = 0; k < 3; ++k) {
+          float pm = 0;
+          CU(cudaEventElapsedTime(&pm, scene->phaseEv[k], scene->phaseEv[k + 1]));
+          stats->phase_ms[k] = pm;             // first band only
+        }
+      }
+      stats->launches = launches;
+      stats->tiles = ts.n;
+      stats->h2d_bytes = (plan.wavefront ? sizeof(WavefrontParams) : sizeof(RenderParams)) * (uint64_t)launches;
+      stats->d2h_bytes = d2h;
+      stats->wall_ms = nowMs() - w0;
+    }
     return YAHR_OK;
   } catch (const CudaFailure& f) {
     return cudaFail(f);
   } catch (const std::exception& e) {
     return fail(YAHR_ERR_INTERNAL, e.what());
   }
+}
+
+// Pinned host memory for the output buffers: device-to-host copies into it run at full PCIe speed
+// and overlap with rendering (pageable memory works too, but the copies are then staged).
+int yahr_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(YAHR_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (yahr_b200_device_count() < 1) return fail(YAHR_ERR_NO_DEVICE, "no CUDA device available");
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(YAHR_ERR_OUT_OF_MEMORY, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return YAHR_OK;
+}
+
+int yahr_b200_host_free(void* p) {
+  if (!p) return YAHR_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return fail(YAHR_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+  return YAHR_OK;
 }
 
 int64_t yahr_b200_num_batches(int64_t num_threads, int64_t width, int64_t height) {

@@ -6,7 +6,10 @@
 namespace yb {
 
 // Flattened scene (see DESIGN.md "Data layout in HBM").
-//   nodes     : 4 x float4 per inner node  = {left box, right box, left ref, right ref}        64 B
+//   nodes     : 4 x float4 per inner node                                                      64 B
+//                 (L.lo.x L.lo.y L.hi.x L.hi.y) (R.lo.x R.lo.y R.hi.x R.hi.y)
+//                 (L.lo.z L.hi.z R.lo.z R.hi.z) (left ref, right ref, -, -)
+//               components are paired so that the slab arithmetic runs as packed f32x2 ops
 //   prims     : 3 x float4 per primitive in left-first DFS leaf order                          48 B
 //                 triangle: A = (p0.xyz, meta)  B = (e1.xyz, primitive ID)  C = (e2.xyz, 0)
 //                 sphere  : A = (c.xyz,  meta)  B = (r, 0, 0, primitive ID) C unused
@@ -55,11 +58,14 @@ struct RenderParams {
 struct WavefrontParams {
   RenderParams base;
   const uint32_t* tileStart;  // nTiles + 1 prefix sums of the tile pixel counts
-  uint32_t nItems;
+  uint32_t nItems;            // items of this launch (a range of tiles)
+  uint32_t itemBase;          // tileStart value of the first tile of this launch
   uint32_t sample;            // sample index of this pass (spp > 1 runs one pass per sample)
   uint32_t dense;             // several lights: shadow slots entry = item * nLights + light
-  float* hitT;                // per item: t of the closest hit
-  uint32_t* hitIdx;           // per item: DFS position of the closest hit (0xFFFFFFFF = miss)
+  uint32_t leafThreshold;     // leaf parking: run the leaf code once this many lanes hold a leaf
+  uint32_t blocksPerSM;       // tuning: persistent CTAs per SM (0 = as many as fit)
+  uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)
+  uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)

@@ -144,8 +144,8 @@ __device__ __forceinline__ uint32_t traverse(const DeviceScene& sc, const Ray& r
       const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
       float keyL, keyR;
       const uint32_t refL = __float_as_uint(n3.x), refR = __float_as_uint(n3.y);
-      const bool passL = boxTest(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r, tMax, keyL) && refL != kDevRefNull;
-      const bool passR = boxTest(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r, tMax, keyR) && refR != kDevRefNull;
+      const bool passL = boxTest(n0.x, n0.y, n2.x, n0.z, n0.w, n2.y, r, tMax, keyL) && refL != kDevRefNull;
+      const bool passR = boxTest(n1.x, n1.y, n2.z, n1.z, n1.w, n2.w, r, tMax, keyR) && refR != kDevRefNull;
       if (passL && passR) {
         if (ORDERED && keyR < keyL) {
           stack[sp++] = make_uint2(refL, __float_as_uint(keyL));

@@ -1,22 +1,23 @@
 // wavefront.cu -- persistent-thread wavefront kernel set (recursion depth 1 = direct lighting, the
 // mode of every BASELINE config).  Compile with --fmad=false.
 //
-//   k_wf_primary : persistent warps pull work items (pixels in tile-major order) from a global counter,
-//                  generate the camera ray (A3) and run the closest-hit walk (A4-A8).  Lanes whose ray
-//                  has finished are refilled with new items (ballot + popc compaction, one atomic per
-//                  warp) so the traversal loop keeps running with a full warp.  Output: (t, DFS position)
-//                  per item.
-//   k_wf_shade   : one thread per item: DifferentialGeometry, material, BSDF per light (A9-A13);
-//                  writes the pixel's base value and appends one shadow-probe record per light with a
-//                  non-zero BSDF (Integrators.hs:59) to a queue (warp-aggregated append).
-//   k_wf_shadow  : persistent warps with the same refill scheme run any-hit walks over the compacted
-//                  queue; an unoccluded probe adds its contribution to the pixel (single light) or sets
-//                  its visibility flag (several lights; k_wf_resolve sums them in light order).
+//   k_wf_primary : persistent warps pull batches of 32 work items (pixels, tile-major order, 8x4 pixel
+//                  footprint per warp) from a global counter, generate the camera rays (A3), run the
+//                  closest-hit walk (A4-A8) and -- once the whole warp has converged -- shade the hits
+//                  (A9-A13): DifferentialGeometry, material, BSDF per light; the pixel's base value is
+//                  stored and one shadow-probe record per light with a non-zero BSDF
+//                  (Integrators.hs:59) is appended to a queue (ballot/popc compaction, one atomic per warp).
+//   k_wf_shadow  : persistent warps run any-hit walks over the compacted queue; an unoccluded probe
+//                  writes its contribution to the pixel (single light) or sets its visibility flag
+//                  (several lights; k_wf_resolve then sums a pixel's lights in light order).
 //   k_wf_accum   : spp > 1 only: acc += sample, and the final divide.
 //
-// The walk is the reference's (left child first, test on entry with the current tMax, later hit
-// replaces), organised as while-while: all lanes descend inner nodes until each holds a leaf, then the
-// leaf code runs once for the whole warp.
+// The walk is the reference's (left child first, box test on entry with the current tMax, later hit
+// replaces).  Rays visit ~20 inner nodes per leaf, so at any moment only a few lanes of a warp hold a
+// leaf; running the (long) primitive-test code for them every round wastes most of the warp.  Lanes
+// that reach a leaf therefore PARK until at least `leafThreshold` lanes hold one (or no lane has inner
+// work left); then the leaf code runs once for all of them.  Parking only delays a lane -- each ray
+// still executes its own steps in the reference order, so results are unchanged.
 #include "kernels.hpp"
 #include "render_device.cuh"
 
@@ -27,7 +28,6 @@ using namespace dev;
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kRefillThreshold = 20;   // leave the traversal loop when fewer lanes than this are busy
 
 struct Trav {
   uint32_t cur;
@@ -54,34 +54,84 @@ __device__ __forceinline__ bool travBegin(const DeviceScene& sc, const Ray& r, f
   return boxTest(sc.rootLo[0], sc.rootLo[1], sc.rootLo[2], sc.rootHi[0], sc.rootHi[1], sc.rootHi[2], r, tMax, key);
 }
 
-// One while-while round.  Returns true when the walk is finished.
-template <bool ANY_HIT, bool ORDERED>
-__device__ __forceinline__ bool travRound(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack) {
-  // ---- descend inner nodes until this lane holds a leaf -------------------------------------
-  while (!(s.cur & kDevRefLeafBit)) {
-    const float4* np = sc.nodes + 4 * (size_t)s.cur;
-    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-    float keyL, keyR;
-    const uint32_t refL = __float_as_uint(n3.x), refR = __float_as_uint(n3.y);
-    const bool passL = boxTest(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r, s.tMax, keyL) && refL != kDevRefNull;
-    const bool passR = boxTest(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r, s.tMax, keyR) && refR != kDevRefNull;
-    if (passL && passR) {
-      if (ORDERED && keyR < keyL) {
-        stack[s.sp++] = make_uint2(refL, __float_as_uint(keyL));
-        s.cur = refR;
-      } else {
-        stack[s.sp++] = make_uint2(refR, __float_as_uint(keyR));
-        s.cur = refL;
-      }
-    } else if (passL) {
-      s.cur = refL;
-    } else if (passR) {
-      s.cur = refR;
-    } else if (!popNext(s, stack)) {
-      return true;
-    }
+// Ray constants of the packed slab test: (-o) and 1/u as register pairs for FADD2 / FMUL2.
+struct RayPack {
+  float2 negOxy, negOzz, invXy, invZz;
+};
+__device__ __forceinline__ RayPack packRay(const Ray& r) {
+  RayPack p;
+  p.negOxy = make_float2(-r.o.x, -r.o.y);
+  p.negOzz = make_float2(-r.o.z, -r.o.z);
+  p.invXy = make_float2(r.inv.x, r.inv.y);
+  p.invZz = make_float2(r.inv.z, r.inv.z);
+  return p;
+}
+
+// Octant of a ray whose 1/u components are all finite: bit k set <=> 1/u_k < 0.
+__device__ __forceinline__ int rayOctant(const Ray& r) {
+  return (r.inv.x < 0.0f ? 1 : 0) | (r.inv.y < 0.0f ? 2 : 0) | (r.inv.z < 0.0f ? 4 : 0);
+}
+
+// Both child box tests of one node for a ray of octant OCT (all 1/u components finite, so no NaN
+// can occur and key = tNear).  Same arithmetic as bbRayIntersection (AABBs.hs:29-40):
+//   t = (b - o) * (1/u)  as  (b + (-o)) * inv  -- identical in IEEE, done as packed f32x2 ops;
+//   min t0 t1 / max t0 t1: for 1/u > 0 the subtraction and the multiplication are monotone, so
+//   t0 <= t1 and the min IS t0 (1/u < 0: t1).  The octant picks them at compile time.
+template <int OCT>
+__device__ __forceinline__ void childTestsOct(const float4& n0, const float4& n1, const float4& n2, const RayPack& p,
+                                              float tMax, bool& passL, float& keyL, bool& passR, float& keyR) {
+  const float2 l0 = __fmul2_rn(__fadd2_rn(make_float2(n0.x, n0.y), p.negOxy), p.invXy);   // L: t0x t0y
+  const float2 l1 = __fmul2_rn(__fadd2_rn(make_float2(n0.z, n0.w), p.negOxy), p.invXy);   // L: t1x t1y
+  const float2 r0 = __fmul2_rn(__fadd2_rn(make_float2(n1.x, n1.y), p.negOxy), p.invXy);   // R: t0x t0y
+  const float2 r1 = __fmul2_rn(__fadd2_rn(make_float2(n1.z, n1.w), p.negOxy), p.invXy);   // R: t1x t1y
+  const float2 lz = __fmul2_rn(__fadd2_rn(make_float2(n2.x, n2.y), p.negOzz), p.invZz);   // L: t0z t1z
+  const float2 rz = __fmul2_rn(__fadd2_rn(make_float2(n2.z, n2.w), p.negOzz), p.invZz);   // R: t0z t1z
+  constexpr bool NX = (OCT & 1) != 0, NY = (OCT & 2) != 0, NZ = (OCT & 4) != 0;
+  const float tNL = fmaxf(fmaxf(fmaxf(0.0f, NX ? l1.x : l0.x), NY ? l1.y : l0.y), NZ ? lz.y : lz.x);
+  const float tFL = fminf(fminf(fminf(tMax, NX ? l0.x : l1.x), NY ? l0.y : l1.y), NZ ? lz.x : lz.y);
+  const float tNR = fmaxf(fmaxf(fmaxf(0.0f, NX ? r1.x : r0.x), NY ? r1.y : r0.y), NZ ? rz.y : rz.x);
+  const float tFR = fminf(fminf(fminf(tMax, NX ? r0.x : r1.x), NY ? r0.y : r1.y), NZ ? rz.x : rz.y);
+  keyL = tNL; passL = tNL <= tFL;
+  keyR = tNR; passR = tNR <= tFR;
+}
+
+// One inner-node visit.  OCT in 0..7: every busy lane of the warp has that octant (packed fast path);
+// OCT = -1: generic path (mixed octants, or some ray whose slab products can be NaN).
+// Returns false when the walk is finished (nothing left to visit).
+template <bool ORDERED, int OCT>
+__device__ __forceinline__ bool innerStep(const DeviceScene& sc, const Ray& r, const RayPack& rp, Trav& s,
+                                          uint2* stack) {
+  const float4* np = sc.nodes + 4 * (size_t)s.cur;
+  const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+  float keyL, keyR;
+  bool passL, passR;
+  const uint32_t refL = __float_as_uint(n3.x), refR = __float_as_uint(n3.y);
+  if (OCT >= 0) {
+    childTestsOct<(OCT >= 0 ? OCT : 0)>(n0, n1, n2, rp, s.tMax, passL, keyL, passR, keyR);
+  } else {
+    passL = boxTest(n0.x, n0.y, n2.x, n0.z, n0.w, n2.y, r, s.tMax, keyL);
+    passR = boxTest(n1.x, n1.y, n2.z, n1.z, n1.w, n2.w, r, s.tMax, keyR);
   }
-  // ---- leaf ----------------------------------------------------------------------------------
+  passL = passL && refL != kDevRefNull;
+  passR = passR && refR != kDevRefNull;
+  if (passL && passR) {
+    if (ORDERED && keyR < keyL) {
+      stack[s.sp++] = make_uint2(refL, __float_as_uint(keyL));
+      s.cur = refR;
+    } else {
+      stack[s.sp++] = make_uint2(refR, __float_as_uint(keyR));
+      s.cur = refL;
+    }
+    return true;
+  }
+  if (passL) { s.cur = refL; return true; }
+  if (passR) { s.cur = refR; return true; }
+  return popNext(s, stack);
+}
+
+// One leaf visit (collideAll over the leaf's primitives in order).  Returns false when finished.
+template <bool ANY_HIT, bool ORDERED>
+__device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack) {
   uint32_t first, count;
   if ((s.cur & kDevRefMultiBits) == kDevRefMultiBits) {
     const uint2 ml = __ldg(&sc.multiLeaves[s.cur & 0x3FFFFFFFu]);
@@ -95,29 +145,80 @@ __device__ __forceinline__ bool travRound(const DeviceScene& sc, const Ray& r, T
     if (hitPrimitive(sc, idx, r, s.tMax, t)) {
       if (!ORDERED || t < s.tMax || s.best == kNoHit || idx > s.best) {
         s.best = idx; s.tMax = t;
-        if (ANY_HIT) return true;
+        if (ANY_HIT) return false;
       }
     }
   }
-  return !popNext(s, stack);
+  return popNext(s, stack);
+}
+
+// Runs the walks of a whole warp to completion with leaf parking.  `busy` per lane.
+template <bool ANY_HIT, bool ORDERED, int OCT>
+__device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+                                             int leafThreshold) {
+  const RayPack rp = packRay(r);
+  for (;;) {
+    const bool atLeaf = busy && (s.cur & kDevRefLeafBit);
+    const bool atInner = busy && !atLeaf;
+    const unsigned mLeaf = __ballot_sync(kFull, atLeaf);
+    const unsigned mInner = __ballot_sync(kFull, atInner);
+    if ((mLeaf | mInner) == 0) break;
+    if (mInner == 0 || __popc(mLeaf) >= leafThreshold) {
+      if (atLeaf) busy = leafStep<ANY_HIT, ORDERED>(sc, r, s, stack);
+    }
+    if (atInner) busy = innerStep<ORDERED, OCT>(sc, r, rp, s, stack);
+  }
+}
+
+// Picks the octant-specialised walk when every busy lane of the warp shares one octant and no lane
+// can produce NaN slab products; otherwise the generic walk.
+template <bool ANY_HIT, bool ORDERED>
+__device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+                                             int leafThreshold, bool packed) {
+  const unsigned mBusy = __ballot_sync(kFull, busy);
+  if (mBusy == 0) return;
+  int oct = -1;
+  if (packed) {
+    const int mine = rayOctant(r);
+    const int lead = __shfl_sync(kFull, mine, __ffs(mBusy) - 1);
+    if (__all_sync(kFull, !busy || (mine == lead && !r.exactNaN))) oct = lead;
+  }
+  switch (oct) {
+    case 0: traverseWarpOct<ANY_HIT, ORDERED, 0>(sc, r, s, stack, busy, leafThreshold); break;
+    case 1: traverseWarpOct<ANY_HIT, ORDERED, 1>(sc, r, s, stack, busy, leafThreshold); break;
+    case 2: traverseWarpOct<ANY_HIT, ORDERED, 2>(sc, r, s, stack, busy, leafThreshold); break;
+    case 3: traverseWarpOct<ANY_HIT, ORDERED, 3>(sc, r, s, stack, busy, leafThreshold); break;
+    case 4: traverseWarpOct<ANY_HIT, ORDERED, 4>(sc, r, s, stack, busy, leafThreshold); break;
+    case 5: traverseWarpOct<ANY_HIT, ORDERED, 5>(sc, r, s, stack, busy, leafThreshold); break;
+    case 6: traverseWarpOct<ANY_HIT, ORDERED, 6>(sc, r, s, stack, busy, leafThreshold); break;
+    case 7: traverseWarpOct<ANY_HIT, ORDERED, 7>(sc, r, s, stack, busy, leafThreshold); break;
+    default: traverseWarpOct<ANY_HIT, ORDERED, -1>(sc, r, s, stack, busy, leafThreshold); break;
+  }
 }
 
 // item index (tile-major) -> tile.  Tiles are almost uniform in size, so a proportional guess is
 // off by a step or two at most.
 __device__ __forceinline__ uint32_t tileOfItem(const WavefrontParams& W, uint32_t item) {
+  const uint32_t g = item + W.itemBase;
   uint32_t t = (uint32_t)(((unsigned long long)item * W.base.nTiles) / W.nItems);
-  while (__ldg(&W.tileStart[t]) > item) --t;
-  while (__ldg(&W.tileStart[t + 1]) <= item) ++t;
+  while (__ldg(&W.tileStart[t]) > g) --t;
+  while (__ldg(&W.tileStart[t + 1]) <= g) ++t;
   return t;
 }
 
+// Pixel of an item.  Inside a tile the items run over strips of 4 rows, column by column, so that
+// 32 consecutive items (one warp) cover an 8 x 4 pixel block.  (The reference's own order inside a
+// tile, u-major (Sampling.hs:6), only matters for its list layout, not for the image.)
 __device__ __forceinline__ void itemPixel(const WavefrontParams& W, uint32_t item, int& u, int& v) {
   const uint32_t t = tileOfItem(W, item);
   const int4 win = __ldg(&W.base.tiles[t]);
-  const int i = (int)(item - __ldg(&W.tileStart[t]));
-  const int th = win.w - win.y;
-  u = win.x + i / th;                                 // u-major inside the tile (Sampling.hs:6)
-  v = win.y + i % th;
+  const int i = (int)(item + W.itemBase - __ldg(&W.tileStart[t]));
+  const int tw = win.z - win.x, th = win.w - win.y;
+  const int strip = i / (4 * tw);
+  const int rem = i - strip * 4 * tw;
+  const int rows = min(4, th - 4 * strip);
+  u = win.x + rem / rows;
+  v = win.y + 4 * strip + rem % rows;
 }
 
 __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, uint32_t sample) {
@@ -127,89 +228,27 @@ __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, u
   return cameraRay(W.base, fu, fv);
 }
 
-}  // namespace
-
-// ---------------------------------------------------------------------------------------------
-template <bool ORDERED>
-__global__ void __launch_bounds__(128) k_wf_primary(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned ltMask = (1u << lane) - 1u;
-  bool busy = false, exhausted = false;      // exhausted is warp-uniform
-  uint32_t item = 0;
-  Ray r;
-  Trav s;
-  s.cur = 0; s.sp = 0; s.tMax = 0; s.best = kNoHit;
-  for (;;) {
-    // ---- refill idle lanes with new work items ----------------------------------------------
-    const unsigned idle = __ballot_sync(kFull, !busy);
-    if (idle && !exhausted) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&W.work[0], (uint32_t)__popc(idle));
-      base = __shfl_sync(kFull, base, 0);
-      exhausted = base + (uint32_t)__popc(idle) >= W.nItems;
-      if (!busy) {
-        const uint32_t mine = base + __popc(idle & ltMask);
-        if (mine < W.nItems) {
-          item = mine;
-          int u, v;
-          itemPixel(W, item, u, v);
-          r = itemRay(W, u, v, W.sample);
-          busy = travBegin(W.base.sc, r, 1e6f, s);
-          if (!busy) { W.hitT[item] = 0.0f; W.hitIdx[item] = kNoHit; }
-        }
-      }
-    }
-    if (!__any_sync(kFull, busy)) {
-      if (exhausted) break;                   // queue drained and nothing in flight
-      continue;
-    }
-    // ---- traverse until too few lanes are busy ----------------------------------------------
-    const int threshold = exhausted ? 1 : kRefillThreshold;
-    do {
-      if (busy) {
-        if (travRound<false, ORDERED>(W.base.sc, r, s, stack)) {
-          W.hitT[item] = s.tMax;
-          W.hitIdx[item] = s.best;
-          busy = false;
-        }
-      }
-    } while (__popc(__ballot_sync(kFull, busy)) >= threshold);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WavefrontParams W) {
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31u;
-  const bool valid = item < W.nItems;
+// Shades the hit of one lane (all 32 lanes call this together) and emits its shadow probes.
+// vhit / directIllumination (Integrators.hs:32-61) up to the point where `reachable` is needed.
+__device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool valid, uint32_t item, uint32_t pixel,
+                                             const Ray& r, float tHit, uint32_t idx, unsigned lane) {
   const DeviceScene& sc = W.base.sc;
-  V3 x = mk(0, 0, 0);
+  const bool hit = valid && idx != kNoHit;
   Surface surf;
   Frame fr;
   MaterialD mat;
-  uint32_t pixel = 0;
-  bool hit = false;
   uint32_t nanBits = 0;
-  V3 wo = mk(0, 0, 0);
+  V3 wo = vneg(r.d);
   if (valid) {
-    int u, v;
-    itemPixel(W, item, u, v);
-    pixel = (uint32_t)(W.base.width * v + u);
-    const uint32_t idx = W.hitIdx[item];
     float* out = W.sampleOut + 3 * (size_t)pixel;
-    if (idx == kNoHit) {
-      out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;
+    if (!hit) {
+      out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;              // Nothing -> Vec3 0 0 0
       if (W.base.primid && W.sample == 0) W.base.primid[pixel] = kNoHit;
     } else {
-      hit = true;
-      const Ray r = itemRay(W, u, v, W.sample);
-      surf = surfaceAt(sc, idx, r, W.hitT[item]);
+      surf = surfaceAt(sc, idx, r, tHit);
       if (W.base.primid && W.sample == 0) W.base.primid[pixel] = surf.primId;
       mat = loadMaterial(sc, surf.material);
       fr = makeFrame(surf);
-      wo = vneg(r.d);
-      x = surf.x;
       // ((n . r) @* f r) * rs with rs = vcast 0 = 0 (Integrators.hs:26,37,41-43): +-0, or NaN when the
       // weight is not finite.  Stored as the pixel's base value; the direct term is added to it.
       const V3 refl = vsub(r.d, vscale(2.0f * dot(r.d, surf.n), surf.n));
@@ -219,9 +258,8 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Wavefr
       nanBits = (base.x != base.x ? 1u : 0u) | (base.y != base.y ? 2u : 0u) | (base.z != base.z ? 4u : 0u);
     }
   }
-  // ---- emit shadow probes: one per light with lensq k > 0 ------------------------------------
-  // single light: compacted queue (warp-aggregated append).  several lights: dense slots
-  // entry = item * nLights + light so that k_wf_resolve can sum a pixel's lights in order.
+  // one probe per light with lensq k > 0.  single light: compacted queue (warp-aggregated append);
+  // several lights: dense slots entry = item * nLights + light so that k_wf_resolve can sum in order.
   uint32_t nEmit = 0;
   for (uint32_t li = 0; li < sc.nLights; ++li) {
     bool emit = false;
@@ -229,12 +267,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Wavefr
     if (hit) {
       const V3 lightPos = xyz(__ldg(&sc.lights[2 * li + 0]));
       const V3 spectrum = xyz(__ldg(&sc.lights[2 * li + 1]));
-      const V3 pointToLight = vsub(lightPos, x);
+      const V3 pointToLight = vsub(lightPos, surf.x);
       const V3 lightDir = vnorm(pointToLight);
       const V3 k = bsdfAt(mat, fr, lightDir, wo);
       if (lensq(k) > 0.0f) {
         emit = true;
-        p0 = vadd(x, vscale(0.001f, lightDir));
+        p0 = vadd(surf.x, vscale(0.001f, lightDir));
         dl = vsub(lightPos, p0);
         const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
         contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
@@ -262,14 +300,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Wavefr
       ++nEmit;
     }
   }
-  // shadow-ray count for the stats
-  const uint32_t warpEmit = __reduce_add_sync(kFull, nEmit);
+  const uint32_t warpEmit = __reduce_add_sync(kFull, nEmit);    // shadow-ray count for the stats
   if (lane == 0 && warpEmit) atomicAdd(&W.work[3], warpEmit);
 }
 
-// ---------------------------------------------------------------------------------------------
 // Result of one shadow probe.  Single light: the pixel holds its base value (+-0 or NaN, written by
-// k_wf_shade); an unoccluded probe overwrites it with base + (0 + contribution), which is the
+// the shading step); an unoccluded probe overwrites it with base + (0 + contribution), which is the
 // contribution itself unless the base is NaN (flag bits in q2.w) -- no read-modify-write, so the
 // frame may live in a peer GPU.  Several lights: only the visibility flag is recorded.
 __device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t entry, bool unoccluded) {
@@ -284,52 +320,65 @@ __device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t 
   out[2] = (nanBits & 4u) ? qnan : 0.0f + c.z;
 }
 
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+template <bool ORDERED, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
+  uint2 stack[64];
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[0], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= W.nItems) break;
+    const uint32_t item = base + lane;
+    const bool valid = item < W.nItems;
+    int u = 0, v = 0;
+    Ray r;
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    bool busy = false;
+    if (valid) {
+      itemPixel(W, item, u, v);
+      r = itemRay(W, u, v, W.sample);
+      busy = travBegin(W.base.sc, r, 1e6f, s);
+    } else {
+      r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    }
+    traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    shadeAndEmit(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <bool ORDERED>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned ltMask = (1u << lane) - 1u;
   const uint32_t nEntries = W.dense ? W.nItems * W.base.sc.nLights : W.work[2];
-  bool busy = false, exhausted = false;
-  uint32_t entry = 0;
-  Ray r;
-  Trav s;
-  s.cur = 0; s.sp = 0; s.tMax = 0; s.best = kNoHit;
   for (;;) {
-    const unsigned idle = __ballot_sync(kFull, !busy);
-    if (idle && !exhausted) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&W.work[1], (uint32_t)__popc(idle));
-      base = __shfl_sync(kFull, base, 0);
-      exhausted = base + (uint32_t)__popc(idle) >= nEntries;
-      if (!busy) {
-        const uint32_t mine = base + __popc(idle & ltMask);
-        if (mine < nEntries) {
-          entry = mine;
-          const float4 a = W.q0[entry], b = W.q1[entry];
-          if (a.w < 0.0f) {                      // empty dense slot
-            W.visibility[entry] = 0;
-          } else {
-            r = makeRay(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z));
-            busy = travBegin(W.base.sc, r, a.w, s);
-            if (!busy) shadowResult(W, entry, true);   // the root box already rejects the probe
-          }
-        }
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[1], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= nEntries) break;
+    const uint32_t entry = base + lane;
+    Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    bool busy = false, probe = false;
+    if (entry < nEntries) {
+      const float4 a = W.q0[entry], b = W.q1[entry];
+      if (a.w < 0.0f) {
+        W.visibility[entry] = 0;                       // empty dense slot
+      } else {
+        probe = true;
+        r = makeRay(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z));
+        busy = travBegin(W.base.sc, r, a.w, s);
       }
     }
-    if (!__any_sync(kFull, busy)) {
-      if (exhausted) break;
-      continue;
-    }
-    const int threshold = exhausted ? 1 : kRefillThreshold;
-    do {
-      if (busy) {
-        if (travRound<true, ORDERED>(W.base.sc, r, s, stack)) {
-          busy = false;
-          shadowResult(W, entry, s.best == kNoHit);
-        }
-      }
-    } while (__popc(__ballot_sync(kFull, busy)) >= threshold);
+    traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    if (probe) shadowResult(W, entry, s.best == kNoHit);
   }
 }
 
@@ -371,16 +420,25 @@ __global__ void __launch_bounds__(256) k_wf_accum(const __grid_constant__ Wavefr
 }
 
 __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
-  // ray counters for the stats: primary = items, shadow = queue length
+  // ray counters for the stats: primary = items, shadow = probes emitted
   atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems);
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
+}
+
+// Persistent launch: exactly as many 128-thread CTAs as can be resident (occupancy API), so that every
+// CTA is scheduled in the first wave and pulls work until the queue is empty.
+static void launchPersistent(void (*kernel)(WavefrontParams), const WavefrontParams& W, int numSMs,
+                             cudaStream_t stream) {
+  int perSM = 0;
+  if (W.blocksPerSM) perSM = (int)W.blocksPerSM;
+  else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 128, 0) != cudaSuccess || perSM < 1) perSM = 8;
+  kernel<<<numSMs * perSM, 128, 0, stream>>>(W);
 }
 
 cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
                             cudaEvent_t* phaseEvents) {
   if (W.nItems == 0) return cudaSuccess;
   const bool ordered = W.base.traversal == 1;
-  const int persistentBlocks = numSMs * 8;             // 128-thread CTAs, up to 8 resident per SM
   const uint32_t itemBlocks = (W.nItems + 255u) / 256u;
   for (int s = 0; s < W.base.spp; ++s) {
     W.sample = (uint32_t)s;
@@ -389,15 +447,14 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     if (e != cudaSuccess) return e;
     const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
     if (timed) cudaEventRecord(phaseEvents[0], stream);
-    if (ordered) k_wf_primary<true><<<persistentBlocks, 128, 0, stream>>>(W);
-    else k_wf_primary<false><<<persistentBlocks, 128, 0, stream>>>(W);
+    launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8> : k_wf_primary<false, 8>)
+                                    : (ordered ? k_wf_primary<true, 1> : k_wf_primary<false, 1>),
+                     W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
-    k_wf_shade<<<itemBlocks, 256, 0, stream>>>(W);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
-    if (ordered) k_wf_shadow<true><<<persistentBlocks, 128, 0, stream>>>(W);
-    else k_wf_shadow<false><<<persistentBlocks, 128, 0, stream>>>(W);
+    launchPersistent(ordered ? k_wf_shadow<true> : k_wf_shadow<false>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
-    if (launches) *launches += 3;
+    if (launches) *launches += 2;
     if (W.dense) { k_wf_resolve<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
     if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
     k_wf_count<<<1, 1, 0, stream>>>(W);

@@ -93,13 +93,13 @@ class TileShardedRenderer:
         del cudart
         return t.data_ptr() - base.value
 
-    def render(self, recursion_depth=1, spp=1, seed=0, traversal=api.TRAVERSAL_REFERENCE, kernel=0):
+    def render(self, recursion_depth=1, spp=1, seed=0, traversal=api.TRAVERSAL_REFERENCE, kernel=0, tune=0):
         """Enqueue one frame on the current stream; the frame is complete on rank 0 once the
         stream has drained.  Returns nothing (no host sync)."""
         torch, dist = self.torch, self.dist
         stream = torch.cuda.current_stream().cuda_stream
         kw = dict(recursion_depth=recursion_depth, spp=spp, seed=seed, traversal=traversal, stream=stream,
-                  stats=False, kernel=kernel)
+                  stats=False, kernel=kernel, tune=tune)
         if self.mode == "local":
             self.scene.render_device(self.cam, self.frame.data_ptr(),
                                      self.primid.data_ptr() if self.primid is not None else None, **kw)
