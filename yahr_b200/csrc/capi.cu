@@ -84,8 +84,11 @@ struct yahr_scene {
   // per (width, height, stride, offset) tile lists, uploaded once
   std::map<std::tuple<int, int, int, int>, TileSet> tiles;
   // wavefront scratch (grown on demand): hit records, shadow queue, work counters, spp buffers
-  float4 *wfQ0 = nullptr, *wfQ1 = nullptr, *wfQ2 = nullptr; unsigned char* wfVis = nullptr; size_t wfEntries = 0;
-  uint32_t* wfWork = nullptr;
+  // two slots so that consecutive bands of the host-buffer entry can be in flight on two streams
+  float4 *wfQ0[2] = {nullptr, nullptr}, *wfQ1[2] = {nullptr, nullptr}, *wfQ2[2] = {nullptr, nullptr};
+  unsigned char* wfVis[2] = {nullptr, nullptr};
+  size_t wfEntries[2] = {0, 0};
+  uint32_t* wfWork = nullptr;              // 2 x 8 counters
   float *wfSampleBuf = nullptr, *wfAccum = nullptr; size_t wfPixels = 0;
   int numSMs = 148;
   // frame buffers of the host-buffer entry (grown on demand)
@@ -94,20 +97,20 @@ struct yahr_scene {
   size_t framePixels = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaStream_t renderStream = nullptr, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
+  cudaStream_t renderStream[2] = {nullptr, nullptr}, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
   std::vector<cudaEvent_t> bandEvents;
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
-    cudaFree(wfQ0); cudaFree(wfQ1); cudaFree(wfQ2); cudaFree(wfVis);
+    for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto e : phaseEv) if (e) cudaEventDestroy(e);
     for (auto e : bandEvents) cudaEventDestroy(e);
-    if (renderStream) cudaStreamDestroy(renderStream);
+    for (auto st : renderStream) if (st) cudaStreamDestroy(st);
     if (copyStream) cudaStreamDestroy(copyStream);
   }
 };
@@ -158,6 +161,7 @@ struct FramePlan {
   RenderParams P{};
   WavefrontParams W{};
   bool wavefront = false;
+  uint32_t entriesPerItem = 1;
 };
 
 int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb, uint32_t* d_primid,
@@ -197,16 +201,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
   if (plan.wavefront) {
     WavefrontParams& W = plan.W;
     const uint32_t nL = sc->dev.nLights;
-    const size_t entries = (size_t)ts.nItems * (nL > 1 ? nL : 1);
-    if (entries > sc->wfEntries) {
-      cudaFree(sc->wfQ0); cudaFree(sc->wfQ1); cudaFree(sc->wfQ2); cudaFree(sc->wfVis);
-      sc->wfQ0 = sc->wfQ1 = sc->wfQ2 = nullptr; sc->wfVis = nullptr; sc->wfEntries = 0;
-      CU(cudaMalloc(&sc->wfQ0, entries * sizeof(float4)));
-      CU(cudaMalloc(&sc->wfQ1, entries * sizeof(float4)));
-      CU(cudaMalloc(&sc->wfQ2, entries * sizeof(float4)));
-      CU(cudaMalloc(&sc->wfVis, entries));
-      sc->wfEntries = entries;
-    }
+    plan.entriesPerItem = nL > 1 ? nL : 1;
     const size_t px = (size_t)cs.width * cs.height;
     if (opts->spp > 1 && px > sc->wfPixels) {
       cudaFree(sc->wfSampleBuf); cudaFree(sc->wfAccum); sc->wfSampleBuf = sc->wfAccum = nullptr; sc->wfPixels = 0;
@@ -214,28 +209,44 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
       CU(cudaMalloc(&sc->wfAccum, px * 3 * sizeof(float)));
       sc->wfPixels = px;
     }
-    if (!sc->wfWork) CU(cudaMalloc(&sc->wfWork, 8 * sizeof(uint32_t)));
+    if (!sc->wfWork) {
+      CU(cudaMalloc(&sc->wfWork, 16 * sizeof(uint32_t)));
+      CU(cudaMemset(sc->wfWork, 0, 16 * sizeof(uint32_t)));
+    }
     W.base = P;
     W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
-    W.q0 = sc->wfQ0; W.q1 = sc->wfQ1; W.q2 = sc->wfQ2; W.visibility = nL > 1 ? sc->wfVis : nullptr;
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
     const uint32_t tune = (uint32_t)opts->reserved[0];
     W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 4u;
     W.blocksPerSM = (tune >> 16) & 0xFF;
     W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
-    W.work = sc->wfWork; W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
+    W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
   }
   return YAHR_OK;
 }
 
 // Enqueues the kernels for tiles [first, first + count) of the plan's tile set.
 void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_t count, cudaStream_t stream,
-                  uint32_t* launches, cudaEvent_t* phaseEv) {
+                  uint32_t* launches, cudaEvent_t* phaseEv, int slot = 0) {
   if (count == 0) return;
   const TileSet& ts = *plan.ts;
   if (plan.wavefront) {
     WavefrontParams W = plan.W;
+    const size_t entries = (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) * plan.entriesPerItem;
+    if (entries > sc->wfEntries[slot]) {          // grows only on the first frame of a given size
+      CU(cudaDeviceSynchronize());
+      cudaFree(sc->wfQ0[slot]); cudaFree(sc->wfQ1[slot]); cudaFree(sc->wfQ2[slot]); cudaFree(sc->wfVis[slot]);
+      sc->wfQ0[slot] = sc->wfQ1[slot] = sc->wfQ2[slot] = nullptr; sc->wfVis[slot] = nullptr; sc->wfEntries[slot] = 0;
+      CU(cudaMalloc(&sc->wfQ0[slot], entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfQ1[slot], entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfQ2[slot], entries * sizeof(float4)));
+      CU(cudaMalloc(&sc->wfVis[slot], entries));
+      sc->wfEntries[slot] = entries;
+    }
+    W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot];
+    W.visibility = plan.entriesPerItem > 1 ? sc->wfVis[slot] : nullptr;
+    W.work = sc->wfWork + 8 * slot;
     W.base.tiles = ts.d_tiles + first; W.base.nTiles = count;
     W.tileStart = ts.d_tileStart + first;
     W.itemBase = ts.hostStart[first];
@@ -463,13 +474,18 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
     if (rc) return rc;
     const TileSet& ts = *plan.ts;
     const int W_ = plan.cs.width, H_ = plan.cs.height;
-    if (!scene->renderStream) CU(cudaStreamCreateWithFlags(&scene->renderStream, cudaStreamNonBlocking));
+    for (auto& st : scene->renderStream) if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (!scene->copyStream) CU(cudaStreamCreateWithFlags(&scene->copyStream, cudaStreamNonBlocking));
-    cudaStream_t rs = scene->renderStream, cp = scene->copyStream;
+    cudaStream_t rs = scene->renderStream[0], rs1 = scene->renderStream[1], cp = scene->copyStream;
+    // the scratch queues are shared with yahr_b200_render_device calls that may still be in flight
+    // on a caller stream
+    CU(cudaDeviceSynchronize());
 
     // The frame is rendered in horizontal BANDS of whole tile rows (tiles are numbered row-major over
     // the tile grid, Sampling.hs:16), and every finished band is copied to the caller's buffer on a
-    // second stream while the next band renders, so the device-to-host transfer overlaps traversal.
+    // copy stream while later bands render, so the device-to-host transfer overlaps traversal.  Bands
+    // alternate between two render streams (each with its own shadow queue), so the shadow trace of one
+    // band overlaps the primary trace of the next and the tails of the persistent kernels are filled.
     // spp > 1 accumulates per pixel across sample passes inside a band, which works the same way.
     uint32_t nBands = 1;
     const uint32_t tileRows = ts.gridNx ? ts.n / ts.gridNx : 0;
@@ -487,6 +503,7 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
     uint32_t launches = 0;
     CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
     CU(cudaEventRecord(scene->ev0, rs));
+    if (nBands > 1) CU(cudaStreamWaitEvent(rs1, scene->ev0, 0));     // counters are cleared before any band
     uint64_t d2h = 0;
     for (uint32_t b = 0; b < nBands; ++b) {
       uint32_t first = 0, count = ts.n;
@@ -496,8 +513,9 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
         first = r0 * ts.gridNx; count = (r1 - r0) * ts.gridNx;
         y0 = ts.hostTiles[first].y; y1 = ts.hostTiles[first + count - 1].w;
       }
-      enqueueTiles(scene, plan, first, count, rs, &launches, (b == 0) ? scene->phaseEv : nullptr);
-      CU(cudaEventRecord(scene->bandEvents[b], rs));
+      cudaStream_t bs = (b & 1u) ? rs1 : rs;
+      enqueueTiles(scene, plan, first, count, bs, &launches, (b == 0) ? scene->phaseEv : nullptr, (int)(b & 1u));
+      CU(cudaEventRecord(scene->bandEvents[b], bs));
       CU(cudaStreamWaitEvent(cp, scene->bandEvents[b], 0));
       const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
       CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
@@ -509,6 +527,10 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
                            (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
         d2h += (uint64_t)(y1 - y0) * idBytes;
       }
+    }
+    if (nBands > 1) {                                  // join: the last band of each render stream
+      CU(cudaStreamWaitEvent(rs, scene->bandEvents[nBands - 1], 0));
+      CU(cudaStreamWaitEvent(rs, scene->bandEvents[nBands - 2], 0));
     }
     CU(cudaEventRecord(scene->ev1, rs));
     unsigned long long c[3];

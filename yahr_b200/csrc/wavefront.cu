@@ -423,6 +423,7 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   // ray counters for the stats: primary = items, shadow = probes emitted
   atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems);
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
+  W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0;      // ready for the next launch
 }
 
 // Persistent launch: exactly as many 128-thread CTAs as can be resident (occupancy API), so that every
@@ -443,8 +444,6 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
   for (int s = 0; s < W.base.spp; ++s) {
     W.sample = (uint32_t)s;
     W.sampleOut = W.base.spp == 1 ? W.base.rgb : W.sampleBuf;
-    cudaError_t e = cudaMemsetAsync(W.work, 0, 4 * sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
     const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
     if (timed) cudaEventRecord(phaseEvents[0], stream);
     launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8> : k_wf_primary<false, 8>)
