@@ -160,6 +160,28 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
 int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
                             float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats);
 
+/* Same frame with the reference's output stage applied on the GPU: JuicyPixels' ImageRGBF -> 8-bit
+ * conversion used by savePngImage (main.hs:142), truncate (255 * max 0 (min 1 x)), no gamma.
+ * rgb8_out: W*H*3 bytes, row-major, row 0 = top.  Only a quarter of the bytes cross PCIe. */
+int yahr_b200_render_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                          unsigned char* rgb8_out, yahr_stats* stats);
+
+/* --- scene file: replaces `read sceneFile :: S.Scene` + `S.objects s >>= S.expand` ----------------
+ * (main.hs:115-117, 44; Scene.hs:15-86).  Host-only, no CUDA needed.  `text` is the derived-Read
+ * syntax of Scene (the .yahrr format).  YAHR_ERR_PARSE mirrors "Prelude.read: no parse",
+ * YAHR_ERR_UNKNOWN_MATERIAL mirrors the Map.! failure of main.hs:55. */
+typedef struct yahr_loaded_scene yahr_loaded_scene;
+int yahr_b200_yahrr_load(const char* text, size_t length, yahr_loaded_scene** out);
+void yahr_b200_yahrr_free(yahr_loaded_scene* loaded);
+/* Fills a descriptor that points INTO `loaded` (valid until yahr_b200_yahrr_free), the camera and the
+ * integrator's recursionDepth; any output may be NULL. */
+int yahr_b200_yahrr_describe(const yahr_loaded_scene* loaded, yahr_scene_desc* desc_out, yahr_camera* camera_out,
+                             int* recursion_depth_out);
+
+/* --- output stage helpers (main.hs:142) ---------------------------------------------------------- */
+int yahr_b200_write_png_rgb8(const char* path, const unsigned char* rgb8, int width, int height);
+void yahr_b200_quantize_rgb8_host(const float* rgb, size_t count, unsigned char* out);
+
 /* Pinned host memory for output buffers (optional): device-to-host copies into it run at full PCIe
  * speed and overlap with rendering inside yahr_b200_render.  Any host pointer works as an output. */
 int yahr_b200_host_alloc(size_t bytes, void** out);

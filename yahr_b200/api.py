@@ -254,6 +254,19 @@ class Scene:
                                       pid.ctypes.data if pid is not None else None, C.byref(st)))
         return rgb, pid, st.as_dict()
 
+    def render_rgb8(self, cam, recursion_depth=1, spp=1, seed=0, out=None):
+        """yahr_b200_render_rgb8: the frame with the reference's 8-bit output stage applied on the GPU."""
+        c = make_camera(cam)
+        w, h = int(np.floor(c.imW)), int(np.floor(c.imH))
+        rgb8 = np.empty((h, w, 3), np.uint8) if out is None else out
+        L = lib()
+        L.yahr_b200_render_rgb8.restype = C.c_int
+        L.yahr_b200_render_rgb8.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                            C.POINTER(Stats)]
+        st = Stats()
+        _check(L.yahr_b200_render_rgb8(self._h, C.byref(c), recursion_depth, spp, seed, rgb8.ctypes.data, C.byref(st)))
+        return rgb8, st.as_dict()
+
     def render_device(self, cam, d_rgb, d_primid=None, recursion_depth=1, spp=1, seed=0,
                       traversal=TRAVERSAL_REFERENCE, tile_stride=1, tile_offset=0, stream=None, stats=True,
                       kernel=0, tune=0):
@@ -308,6 +321,64 @@ class HostBvh:
         _check(lib().yahr_b200_host_bvh_preorder(self._h, kinds.ctypes.data_as(_u32p), firsts.ctypes.data_as(_u32p),
                                                  counts.ctypes.data_as(_u32p), boxes.ctypes.data_as(_f32p)))
         return kinds, firsts, counts, boxes
+
+
+def load_yahrr(text):
+    """Parse `.yahrr` text (derived-Read syntax of Scene, Scene.hs:52-58) and apply `expand`
+    (Scene.hs:61-86) with the library's C++ host code.  Returns (scene dict, camera dict, recursionDepth)."""
+    L = lib()
+    L.yahr_b200_yahrr_load.restype = C.c_int
+    L.yahr_b200_yahrr_load.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.yahr_b200_yahrr_free.argtypes = [C.c_void_p]
+    L.yahr_b200_yahrr_describe.restype = C.c_int
+    L.yahr_b200_yahrr_describe.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(Camera), C.POINTER(C.c_int)]
+    data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    h = C.c_void_p()
+    _check(L.yahr_b200_yahrr_load(data, len(data), C.byref(h)))
+    try:
+        d, c, depth = SceneDesc(), Camera(), C.c_int(0)
+        _check(L.yahr_b200_yahrr_describe(h, C.byref(d), C.byref(c), C.byref(depth)))
+
+        def arr(ptr, n, cols, dtype):
+            if n == 0 or not ptr:
+                return np.zeros((0, cols) if cols else (0,), dtype)
+            a = np.ctypeslib.as_array(ptr, shape=(n * max(cols, 1),)).astype(dtype, copy=True)
+            return a.reshape(n, cols) if cols else a
+
+        nt, ns = d.n_triangles, d.n_spheres
+        scene = dict(
+            tri_p0=arr(d.tri_p0, nt, 3, np.float32), tri_p1=arr(d.tri_p1, nt, 3, np.float32),
+            tri_p2=arr(d.tri_p2, nt, 3, np.float32), tri_n0=arr(d.tri_n0, nt, 3, np.float32),
+            tri_n1=arr(d.tri_n1, nt, 3, np.float32), tri_n2=arr(d.tri_n2, nt, 3, np.float32),
+            tri_material=arr(d.tri_material, nt, 0, np.uint32),
+            sph_center=arr(d.sph_center, ns, 3, np.float32), sph_radius=arr(d.sph_radius, ns, 0, np.float32),
+            sph_material=arr(d.sph_material, ns, 0, np.uint32),
+            prim_order=arr(d.prim_order, nt + ns, 0, np.uint32),
+            materials=arr(d.materials, d.n_materials, 7, np.float32), lights=arr(d.lights, d.n_lights, 6, np.float32),
+            bvh_max_depth=int(d.bvh_max_depth), split_mode=int(d.split_mode))
+        cam = dict(imW=float(c.imW), imH=float(c.imH), focalLength=float(c.focalLength),
+                   lookDir=list(c.lookDir), upDir=list(c.upDir), position=list(c.position))
+        return scene, cam, int(depth.value)
+    finally:
+        L.yahr_b200_yahrr_free(h)
+
+
+def write_png_rgb8(path, rgb8):
+    a = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w = a.shape[0], a.shape[1]
+    L = lib()
+    L.yahr_b200_write_png_rgb8.restype = C.c_int
+    L.yahr_b200_write_png_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    _check(L.yahr_b200_write_png_rgb8(path.encode(), a.ctypes.data, w, h))
+
+
+def quantize_rgb8_host(rgb):
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    out = np.empty(a.shape, np.uint8)
+    L = lib()
+    L.yahr_b200_quantize_rgb8_host.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.yahr_b200_quantize_rgb8_host(a.ctypes.data, a.size, out.ctypes.data)
+    return out
 
 
 def camera_matrices(cam):

@@ -17,6 +17,7 @@
 #include "device_types.cuh"
 #include "host_scene.hpp"
 #include "kernels.hpp"
+#include "yahrr_parser.hpp"
 
 using namespace yb;
 
@@ -95,6 +96,8 @@ struct yahr_scene {
   float* d_rgb = nullptr;
   uint32_t* d_primid = nullptr;
   size_t framePixels = 0;
+  unsigned char* d_rgb8 = nullptr;
+  size_t frame8Pixels = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t renderStream[2] = {nullptr, nullptr}, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
@@ -102,7 +105,7 @@ struct yahr_scene {
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
-    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid);
+    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
@@ -117,6 +120,10 @@ struct yahr_scene {
 
 struct yahr_host_bvh {
   HostBvh bvh;
+};
+
+struct yahr_loaded_scene {
+  LoadedScene scene;
 };
 
 namespace {
@@ -447,9 +454,9 @@ int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yah
   }
 }
 
-int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
-                     float* rgb_out, uint32_t* primid_out, yahr_stats* stats) {
-  if (!scene || !cam || !rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                      float* rgb_out, unsigned char* rgb8_out, uint32_t* primid_out, yahr_stats* stats) {
+  if (!scene || !cam || (!rgb_out && !rgb8_out)) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
   try {
     const double w0 = nowMs();
     yahr_render_opts o{};
@@ -467,6 +474,11 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
         CU(cudaMalloc(&scene->d_rgb, px0 * 3 * sizeof(float)));
         CU(cudaMalloc(&scene->d_primid, px0 * sizeof(uint32_t)));
         scene->framePixels = px0;
+      }
+      if (rgb8_out && px0 > scene->frame8Pixels) {
+        cudaFree(scene->d_rgb8); scene->d_rgb8 = nullptr; scene->frame8Pixels = 0;
+        CU(cudaMalloc(&scene->d_rgb8, px0 * 3));
+        scene->frame8Pixels = px0;
       }
     }
     FramePlan plan;
@@ -515,12 +527,25 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
       }
       cudaStream_t bs = (b & 1u) ? rs1 : rs;
       enqueueTiles(scene, plan, first, count, bs, &launches, (b == 0) ? scene->phaseEv : nullptr, (int)(b & 1u));
+      if (rgb8_out) {                                   // output stage on the GPU: 1 byte per channel goes down
+        const size_t rowElems = (size_t)W_ * 3;
+        CU(launchQuantizeRgb8(scene->d_rgb, scene->d_rgb8, (size_t)y0 * rowElems, (size_t)(y1 - y0) * rowElems, bs,
+                              &launches));
+      }
       CU(cudaEventRecord(scene->bandEvents[b], bs));
       CU(cudaStreamWaitEvent(cp, scene->bandEvents[b], 0));
-      const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
-      CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
-                         (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
-      d2h += (uint64_t)(y1 - y0) * rowBytes;
+      if (rgb_out) {
+        const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
+        CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
+                           (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+        d2h += (uint64_t)(y1 - y0) * rowBytes;
+      }
+      if (rgb8_out) {
+        const size_t rowBytes = (size_t)W_ * 3;
+        CU(cudaMemcpyAsync(rgb8_out + (size_t)y0 * rowBytes, scene->d_rgb8 + (size_t)y0 * rowBytes,
+                           (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+        d2h += (uint64_t)(y1 - y0) * rowBytes;
+      }
       if (primid_out) {
         const size_t idBytes = (size_t)W_ * sizeof(uint32_t);
         CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
@@ -562,6 +587,18 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
   } catch (const std::exception& e) {
     return fail(YAHR_ERR_INTERNAL, e.what());
   }
+}
+
+int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                     float* rgb_out, uint32_t* primid_out, yahr_stats* stats) {
+  if (!rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb_out is NULL");
+  return renderHost(scene, cam, recursion_depth, spp, seed, rgb_out, nullptr, primid_out, stats);
+}
+
+int yahr_b200_render_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                          unsigned char* rgb8_out, yahr_stats* stats) {
+  if (!rgb8_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb8_out is NULL");
+  return renderHost(scene, cam, recursion_depth, spp, seed, nullptr, rgb8_out, nullptr, stats);
 }
 
 // Pinned host memory for the output buffers: device-to-host copies into it run at full PCIe speed
@@ -617,6 +654,44 @@ int yahr_b200_ipc_close(void* device_ptr) {
   cudaError_t e = cudaIpcCloseMemHandle(device_ptr);
   if (e != cudaSuccess) return fail(YAHR_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
   return YAHR_OK;
+}
+
+// ---- .yahrr reader + expand (Scene.hs:15-86), output stage (main.hs:142) -------------------------
+int yahr_b200_yahrr_load(const char* text, size_t length, yahr_loaded_scene** out) {
+  if (!text || !out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  try {
+    yahr_loaded_scene* h = new yahr_loaded_scene();
+    std::string err;
+    int rc = loadYahrr(std::string(text, length), h->scene, err);
+    if (rc) { delete h; return fail(rc, err); }
+    *out = h;
+    return YAHR_OK;
+  } catch (const std::exception& e) {
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+
+void yahr_b200_yahrr_free(yahr_loaded_scene* h) { delete h; }
+
+int yahr_b200_yahrr_describe(const yahr_loaded_scene* h, yahr_scene_desc* desc_out, yahr_camera* camera_out,
+                             int* recursion_depth_out) {
+  if (!h) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (desc_out) *desc_out = h->scene.desc();
+  if (camera_out) *camera_out = h->scene.camera;
+  if (recursion_depth_out) *recursion_depth_out = h->scene.recursionDepth;
+  return YAHR_OK;
+}
+
+int yahr_b200_write_png_rgb8(const char* path, const unsigned char* rgb8, int width, int height) {
+  if (!path || !rgb8 || width < 1 || height < 1) return fail(YAHR_ERR_INVALID_ARGUMENT, "invalid argument");
+  std::string err;
+  int rc = writePngRgb8(path, rgb8, width, height, err);
+  return rc ? fail(rc, err) : YAHR_OK;
+}
+
+void yahr_b200_quantize_rgb8_host(const float* rgb, size_t count, unsigned char* out) {
+  for (size_t i = 0; i < count; ++i) out[i] = quantize8(rgb[i]);
 }
 
 // ---- host-only inspection ----------------------------------------------------------------------

@@ -54,6 +54,26 @@ __global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ Ren
   }
 }
 
+// JuicyPixels' ImageRGBF -> 8-bit conversion of savePngImage (main.hs:142): truncate (255 * max 0 (min 1 x)),
+// no gamma; GHC's min/max selects turn NaN into 0.
+__global__ void __launch_bounds__(256) k_quantize_rgb8(const float* __restrict__ rgb, unsigned char* __restrict__ out,
+                                                        size_t first, size_t count) {
+  const size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= first + count) return;
+  const float x = rgb[i];
+  const float m = (1.0f <= x) ? 1.0f : x;
+  const float c = (0.0f <= m) ? m : 0.0f;
+  out[i] = (unsigned char)(int)(255.0f * c);
+}
+
+cudaError_t launchQuantizeRgb8(const float* rgb, unsigned char* out, size_t first, size_t count, cudaStream_t stream,
+                               uint32_t* launches) {
+  if (count == 0) return cudaSuccess;
+  k_quantize_rgb8<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(rgb, out, first, count);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_t* launches) {
   if (P.nTiles == 0) return cudaSuccess;
   if (P.traversal == 1) k_render_mega<true><<<P.nTiles, 256, 0, stream>>>(P);

@@ -7,6 +7,10 @@ namespace yb {
 // One CTA per tile, one thread per pixel, whole per-pixel path inline.
 cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_t* launches);
 
+// float RGB -> 8-bit RGB with JuicyPixels' quantisation, for elements [first, first + count).
+cudaError_t launchQuantizeRgb8(const float* rgb, unsigned char* out, size_t first, size_t count, cudaStream_t stream,
+                               uint32_t* launches);
+
 }  // namespace yb
 
 namespace yb {
