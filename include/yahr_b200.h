@@ -128,6 +128,8 @@ typedef struct yahr_scene_info {
   uint64_t device_bytes;    /* HBM held by the scene */
   double build_ms;          /* host BVH construction (restating Culling.hs:27-112) */
   double upload_ms;
+  uint32_t built_on_device; /* 1: BVH built by the GPU builder, 0: host builder */
+  uint32_t reserved0;
 } yahr_scene_info;
 
 typedef struct yahr_scene yahr_scene;
@@ -143,6 +145,11 @@ const char* yahr_b200_last_error(void);           /* thread-local, never NULL */
 int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out);
 void yahr_b200_scene_destroy(yahr_scene* scene);
 int yahr_b200_scene_info(const yahr_scene* scene, yahr_scene_info* out);
+/* Inspection: download the device-resident BVH.  order_out: n_primitives uint32 (primitive ID per DFS
+ * position); nodes_out: n_nodes x 16 floats (64-byte traversal nodes); multi_out: n_multi_leaves x 2
+ * uint32 (first, count).  Any output may be NULL. */
+int yahr_b200_scene_download_bvh(const yahr_scene* scene, uint32_t* order_out, float* nodes_out, uint32_t* multi_out,
+                                 uint32_t* root_ref_out, float root_box_out[6]);
 
 /* --- render: replaces render / renderEval / renderPar + samplesToImage (main.hs:68-107) -------- */
 /* Host-buffer entry (the call the Haskell host makes).  rgb_out: W*H*3 floats, row-major, RGB

@@ -68,7 +68,7 @@ class Stats(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_primitives", C.c_uint32), ("n_nodes", C.c_uint32), ("n_multi_leaves", C.c_uint32),
                 ("depth", C.c_uint32), ("device_bytes", C.c_uint64), ("build_ms", C.c_double),
-                ("upload_ms", C.c_double)]
+                ("upload_ms", C.c_double), ("built_on_device", C.c_uint32), ("reserved0", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -253,6 +253,21 @@ class Scene:
         _check(lib().yahr_b200_render(self._h, C.byref(c), recursion_depth, spp, seed, rgb.ctypes.data,
                                       pid.ctypes.data if pid is not None else None, C.byref(st)))
         return rgb, pid, st.as_dict()
+
+    def download_bvh(self):
+        """(order[n_prims], nodes[n_nodes,16] float32 raw, multi[n_multi,2], root_ref, root_box[6])."""
+        i = self.info()
+        order = np.zeros(i["n_primitives"], np.uint32)
+        nodes = np.zeros((i["n_nodes"], 16), np.float32)
+        multi = np.zeros((i["n_multi_leaves"], 2), np.uint32)
+        root = C.c_uint32(0)
+        box = np.zeros(6, np.float32)
+        L = lib()
+        L.yahr_b200_scene_download_bvh.restype = C.c_int
+        L.yahr_b200_scene_download_bvh.argtypes = [C.c_void_p] * 4 + [C.POINTER(C.c_uint32), C.c_void_p]
+        _check(L.yahr_b200_scene_download_bvh(self._h, order.ctypes.data, nodes.ctypes.data, multi.ctypes.data,
+                                              C.byref(root), box.ctypes.data))
+        return order, nodes, multi, root.value, box
 
     def render_rgb8(self, cam, recursion_depth=1, spp=1, seed=0, out=None):
         """yahr_b200_render_rgb8: the frame with the reference's 8-bit output stage applied on the GPU."""

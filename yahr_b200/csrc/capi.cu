@@ -14,6 +14,7 @@
 
 #include "../../include/yahr_b200.h"
 #include "bvh_build.hpp"
+#include "bvh_build_gpu.hpp"
 #include "device_types.cuh"
 #include "host_scene.hpp"
 #include "kernels.hpp"
@@ -81,6 +82,7 @@ struct yahr_scene {
   float4* d_materials = nullptr;
   float4* d_lights = nullptr;
   unsigned long long* d_counters = nullptr;
+  uint32_t* d_order = nullptr;            // primitive ID per DFS position (inspection)
   yahr_scene_info info{};
   // per (width, height, stride, offset) tile lists, uploaded once
   std::map<std::tuple<int, int, int, int>, TileSet> tiles;
@@ -105,7 +107,7 @@ struct yahr_scene {
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
-    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
+    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
@@ -305,6 +307,118 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
   return YAHR_OK;
 }
 
+// Small per-scene tables (materials, lights), events, counters: shared by both build paths.
+void uploadSmallTables(yahr_scene* sc, const yahr_scene_desc* desc, uint64_t& bytes) {
+  std::vector<float4> mats(2 * (size_t)desc->n_materials), lights(2 * (size_t)desc->n_lights);
+  for (uint32_t m = 0; m < desc->n_materials; ++m) {
+    const float* s = desc->materials + 7 * (size_t)m;
+    mats[2 * m + 0] = make_float4(s[0], s[1], s[2], s[6]);
+    mats[2 * m + 1] = make_float4(s[3], s[4], s[5], 0.0f);
+  }
+  for (uint32_t l = 0; l < desc->n_lights; ++l) {
+    const float* s = desc->lights + 6 * (size_t)l;
+    lights[2 * l + 0] = make_float4(s[0], s[1], s[2], 0.0f);
+    lights[2 * l + 1] = make_float4(s[3], s[4], s[5], 0.0f);
+  }
+  sc->d_materials = devUpload(mats, bytes);
+  sc->d_lights = devUpload(lights, bytes);
+  CU(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
+  CU(cudaEventCreate(&sc->ev0));
+  CU(cudaEventCreate(&sc->ev1));
+  for (auto& e : sc->phaseEv) CU(cudaEventCreate(&e));
+  sc->dev.materials = sc->d_materials; sc->dev.lights = sc->d_lights; sc->dev.nLights = desc->n_lights;
+}
+
+// Copies one caller array into the input arena (256-byte aligned slices of one stream-ordered allocation).
+template <class T>
+const T* arenaCopy(const T* host, size_t count, char* base, size_t& off) {
+  if (!host || count == 0) return nullptr;
+  off = (off + 255) & ~(size_t)255;
+  T* p = reinterpret_cast<T*>(base + off);
+  off += count * sizeof(T);
+  CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, 0));
+  return p;
+}
+
+// Device build path: upload the caller's arrays as they are, build on the GPU (bvh_build_gpu.cu).
+// Returns YAHR_OK, a positive error code, or -1 when the device builder declines (host builder next).
+int createSceneOnDevice(const yahr_scene_desc* d, yahr_scene** out) {
+  const uint64_t n = (uint64_t)d->n_spheres + d->n_triangles;
+  if (n >= 0x40000000ull) return fail(YAHR_ERR_INVALID_ARGUMENT, "more than 2^30 primitives");
+  if (d->n_triangles && !(d->tri_p0 && d->tri_p1 && d->tri_p2 && d->tri_n0 && d->tri_n1 && d->tri_n2))
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "triangle arrays missing");
+  if (d->n_spheres && !(d->sph_center && d->sph_radius)) return fail(YAHR_ERR_INVALID_ARGUMENT, "sphere arrays missing");
+  if (d->n_materials && !d->materials) return fail(YAHR_ERR_INVALID_ARGUMENT, "materials missing");
+  if (d->n_lights && !d->lights) return fail(YAHR_ERR_INVALID_ARGUMENT, "lights missing");
+  char* inputArena = nullptr;
+  yahr_scene* sc = nullptr;
+  GpuBuildOutput bo;
+  auto cleanup = [&]() { if (inputArena) cudaFreeAsync(inputArena, 0); inputArena = nullptr; };
+  try {
+    const double t0 = nowMs();
+    GpuBuildInput in{};
+    in.nPrims = (uint32_t)n; in.nTriangles = d->n_triangles; in.nSpheres = d->n_spheres; in.nMaterials = d->n_materials;
+    const size_t nt = d->n_triangles, ns = d->n_spheres;
+    const size_t inputBytes = 6 * (3 * nt * 4 + 256) + (nt * 4 + 256) + (3 * ns * 4 + 256) + 2 * (ns * 4 + 256) +
+                              ((size_t)n * 4 + 256) + 256;
+    CU(cudaMallocAsync((void**)&inputArena, inputBytes, 0));
+    size_t off = 0;
+    in.triP0 = arenaCopy(d->tri_p0, 3 * nt, inputArena, off); in.triP1 = arenaCopy(d->tri_p1, 3 * nt, inputArena, off);
+    in.triP2 = arenaCopy(d->tri_p2, 3 * nt, inputArena, off); in.triN0 = arenaCopy(d->tri_n0, 3 * nt, inputArena, off);
+    in.triN1 = arenaCopy(d->tri_n1, 3 * nt, inputArena, off); in.triN2 = arenaCopy(d->tri_n2, 3 * nt, inputArena, off);
+    in.triMaterial = arenaCopy(d->tri_material, nt, inputArena, off);
+    in.sphCenter = arenaCopy(d->sph_center, 3 * ns, inputArena, off);
+    in.sphRadius = arenaCopy(d->sph_radius, ns, inputArena, off);
+    in.sphMaterial = arenaCopy(d->sph_material, ns, inputArena, off);
+    in.primOrder = arenaCopy(d->prim_order, (size_t)n, inputArena, off);
+    CU(cudaStreamSynchronize(0));
+    const double t1 = nowMs();
+    if (!buildBvhOnDevice(in, d->bvh_max_depth, bo)) {
+      cleanup(); freeGpuBuildOutput(bo);
+      throw CudaFailure{bo.error, bo.where, __FILE__, __LINE__};
+    }
+    cleanup();
+    const double t2 = nowMs();
+    if (bo.errorFlags & 4u) { freeGpuBuildOutput(bo); return fail(YAHR_ERR_INVALID_ARGUMENT, "prim_order: index out of range"); }
+    if (bo.errorFlags & 1u) { freeGpuBuildOutput(bo); return fail(YAHR_ERR_NON_FINITE_INPUT, "non-finite geometry"); }
+    if (bo.errorFlags & 2u) {
+      freeGpuBuildOutput(bo);
+      return fail(YAHR_ERR_UNKNOWN_MATERIAL, "material index out of range");     // the reference: Map.! (main.hs:55)
+    }
+    if (bo.unsupported) { freeGpuBuildOutput(bo); return -1; }
+    if (bo.tooDeep || bo.depth + 1 > YAHR_B200_MAX_STACK) {
+      freeGpuBuildOutput(bo);
+      return fail(YAHR_ERR_BVH_TOO_DEEP, "BVH depth " + std::to_string(bo.depth) + " exceeds the traversal stack (" +
+                                             std::to_string(YAHR_B200_MAX_STACK) + ")");
+    }
+    sc = new yahr_scene();
+    CU(cudaGetDevice(&sc->device));
+    CU(cudaDeviceGetAttribute(&sc->numSMs, cudaDevAttrMultiProcessorCount, sc->device));
+    sc->d_nodes = bo.flat; sc->d_prims = bo.prims; sc->d_normals = bo.normals; sc->d_multi = bo.multi;
+    sc->d_order = bo.order;
+    bo.flat = nullptr; bo.prims = nullptr; bo.normals = nullptr; bo.multi = nullptr; bo.order = nullptr;
+    uint64_t bytes = (uint64_t)bo.nInner * 64 + (uint64_t)n * 96 + (uint64_t)bo.nMulti * 8 + (uint64_t)n * 4;
+    uploadSmallTables(sc, d, bytes);
+    sc->dev.nodes = sc->d_nodes; sc->dev.prims = sc->d_prims; sc->dev.normals = sc->d_normals;
+    sc->dev.multiLeaves = sc->d_multi;
+    sc->dev.rootRef = n ? bo.rootRef : kDevRefNull;
+    for (int c = 0; c < 3; ++c) { sc->dev.rootLo[c] = bo.rootBox[c]; sc->dev.rootHi[c] = bo.rootBox[3 + c]; }
+    sc->info.n_primitives = (uint32_t)n; sc->info.n_nodes = bo.nInner; sc->info.n_multi_leaves = bo.nMulti;
+    sc->info.depth = bo.depth; sc->info.device_bytes = bytes;
+    sc->info.build_ms = t2 - t1; sc->info.upload_ms = t1 - t0;
+    sc->info.built_on_device = 1;
+    CU(cudaDeviceSynchronize());
+    *out = sc;
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    cleanup(); freeGpuBuildOutput(bo); delete sc;
+    return cudaFail(f);
+  } catch (const std::bad_alloc&) {
+    cleanup(); freeGpuBuildOutput(bo); delete sc;
+    return fail(YAHR_ERR_OUT_OF_MEMORY, "host out of memory");
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -326,6 +440,14 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
   try {
     if (yahr_b200_device_count() < 1)
       return fail(YAHR_ERR_NO_DEVICE, "no CUDA device available (libyahr_b200 has no CPU fallback)");
+    // Default: build the BVH on the device (Midpoint split).  SurfaceAreaHeuristic, the degenerate
+    // cases the device builder declines, and YAHR_B200_HOST_BUILD=1 use the host builder below.
+    if (desc && gpuBuildSupported(desc->split_mode) && !getenv("YAHR_B200_HOST_BUILD")) {
+      int rcDev = createSceneOnDevice(desc, &sc);
+      if (rcDev == YAHR_OK) { *out = sc; return YAHR_OK; }
+      if (rcDev > 0) return rcDev;          // a real error; rcDev < 0: declined, fall through to the host builder
+      sc = nullptr;
+    }
     std::vector<HostPrim> prims;
     std::vector<Box> bounds;
     std::string err;
@@ -393,6 +515,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     sc->d_multi = devUpload(multi, bytes);
     sc->d_materials = devUpload(mats, bytes);
     sc->d_lights = devUpload(lights, bytes);
+    sc->d_order = devUpload(bvh.order, bytes);
     CU(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaEventCreate(&sc->ev0));
     CU(cudaEventCreate(&sc->ev1));
@@ -413,6 +536,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     sc->info.device_bytes = bytes;
     sc->info.build_ms = t1 - t0;
     sc->info.upload_ms = t3 - t2;
+    sc->info.built_on_device = 0;
     *out = sc;
     return YAHR_OK;
   } catch (const CudaFailure& f) {
@@ -434,6 +558,28 @@ void yahr_b200_scene_destroy(yahr_scene* scene) {
   cudaSetDevice(scene->device);
   delete scene;
   cudaSetDevice(prev);
+}
+
+// Inspection: download the BVH that lives on the device (used to check the GPU builder against the
+// host builder).  Any output may be NULL.  nodes_out: n_nodes x 16 floats (the 64-byte node layout),
+// multi_out: n_multi_leaves x 2 uint32, order_out: n_primitives uint32.
+int yahr_b200_scene_download_bvh(const yahr_scene* scene, uint32_t* order_out, float* nodes_out, uint32_t* multi_out,
+                                 uint32_t* root_ref_out, float root_box_out[6]) {
+  if (!scene) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  try {
+    const yahr_scene_info& i = scene->info;
+    if (order_out && i.n_primitives)
+      CU(cudaMemcpy(order_out, scene->d_order, (size_t)i.n_primitives * 4, cudaMemcpyDeviceToHost));
+    if (nodes_out && i.n_nodes) CU(cudaMemcpy(nodes_out, scene->d_nodes, (size_t)i.n_nodes * 64, cudaMemcpyDeviceToHost));
+    if (multi_out && i.n_multi_leaves)
+      CU(cudaMemcpy(multi_out, scene->d_multi, (size_t)i.n_multi_leaves * 8, cudaMemcpyDeviceToHost));
+    if (root_ref_out) *root_ref_out = scene->dev.rootRef;
+    if (root_box_out)
+      for (int c = 0; c < 3; ++c) { root_box_out[c] = scene->dev.rootLo[c]; root_box_out[3 + c] = scene->dev.rootHi[c]; }
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  }
 }
 
 int yahr_b200_scene_info(const yahr_scene* scene, yahr_scene_info* out) {
