@@ -230,6 +230,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.blocksPerSM = (tune >> 16) & 0xFF;
     W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
+    W.sharedLoop = (tune >> 10) & 1u;              // default: nine specialised loops (bit 10 set = one shared loop;
+                                                   // measured slower: the per-step switch costs more than the I-cache saves)
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
   }
   return YAHR_OK;

@@ -66,6 +66,7 @@ struct WavefrontParams {
   uint32_t blocksPerSM;       // tuning: persistent CTAs per SM (0 = as many as fit)
   uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
+  uint32_t sharedLoop;        // one traversal loop with a switch on the octant (smaller code) vs nine loops
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)

@@ -172,9 +172,10 @@ __device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray
 
 // Picks the octant-specialised walk when every busy lane of the warp shares one octant and no lane
 // can produce NaN slab products; otherwise the generic walk.
-template <bool ANY_HIT, bool ORDERED>
+template <bool ANY_HIT, bool ORDERED, bool SHARED>
 __device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
                                              int leafThreshold, bool packed) {
+  constexpr bool sharedLoop = SHARED;
   const unsigned mBusy = __ballot_sync(kFull, busy);
   if (mBusy == 0) return;
   int oct = -1;
@@ -182,6 +183,35 @@ __device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r
     const int mine = rayOctant(r);
     const int lead = __shfl_sync(kFull, mine, __ffs(mBusy) - 1);
     if (__all_sync(kFull, !busy || (mine == lead && !r.exactNaN))) oct = lead;
+  }
+  if (sharedLoop) {
+    // one loop, one copy of the leaf code; only the node step is specialised (the octant is warp-uniform,
+    // so the switch is a uniform branch).  Keeps the kernel small enough for the instruction cache.
+    const RayPack rp = packRay(r);
+    for (;;) {
+      const bool atLeaf = busy && (s.cur & kDevRefLeafBit);
+      const bool atInner = busy && !atLeaf;
+      const unsigned mLeaf = __ballot_sync(kFull, atLeaf);
+      const unsigned mInner = __ballot_sync(kFull, atInner);
+      if ((mLeaf | mInner) == 0) break;
+      if (mInner == 0 || __popc(mLeaf) >= leafThreshold) {
+        if (atLeaf) busy = leafStep<ANY_HIT, ORDERED>(sc, r, s, stack);
+      }
+      if (atInner) {
+        switch (oct) {
+          case 0: busy = innerStep<ORDERED, 0>(sc, r, rp, s, stack); break;
+          case 1: busy = innerStep<ORDERED, 1>(sc, r, rp, s, stack); break;
+          case 2: busy = innerStep<ORDERED, 2>(sc, r, rp, s, stack); break;
+          case 3: busy = innerStep<ORDERED, 3>(sc, r, rp, s, stack); break;
+          case 4: busy = innerStep<ORDERED, 4>(sc, r, rp, s, stack); break;
+          case 5: busy = innerStep<ORDERED, 5>(sc, r, rp, s, stack); break;
+          case 6: busy = innerStep<ORDERED, 6>(sc, r, rp, s, stack); break;
+          case 7: busy = innerStep<ORDERED, 7>(sc, r, rp, s, stack); break;
+          default: busy = innerStep<ORDERED, -1>(sc, r, rp, s, stack); break;
+        }
+      }
+    }
+    return;
   }
   switch (oct) {
     case 0: traverseWarpOct<ANY_HIT, ORDERED, 0>(sc, r, s, stack, busy, leafThreshold); break;
@@ -323,7 +353,7 @@ __device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, int MIN_BLOCKS>
+template <bool ORDERED, int MIN_BLOCKS, bool SHARED>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
@@ -346,13 +376,13 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
-    traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    traverseWarp<false, ORDERED, SHARED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     shadeAndEmit(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED>
+template <bool ORDERED, bool SHARED>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ Wavef
         busy = travBegin(W.base.sc, r, a.w, s);
       }
     }
-    traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    traverseWarp<true, ORDERED, SHARED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     if (probe) shadowResult(W, entry, s.best == kNoHit);
   }
 }
@@ -446,12 +476,18 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     W.sampleOut = W.base.spp == 1 ? W.base.rgb : W.sampleBuf;
     const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
     if (timed) cudaEventRecord(phaseEvents[0], stream);
-    launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8> : k_wf_primary<false, 8>)
-                                    : (ordered ? k_wf_primary<true, 1> : k_wf_primary<false, 1>),
-                     W, numSMs, stream);
+    if (W.sharedLoop)
+      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, true> : k_wf_primary<false, 8, true>)
+                                      : (ordered ? k_wf_primary<true, 1, true> : k_wf_primary<false, 1, true>),
+                       W, numSMs, stream);
+    else
+      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false> : k_wf_primary<false, 8, false>)
+                                      : (ordered ? k_wf_primary<true, 1, false> : k_wf_primary<false, 1, false>),
+                       W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
-    launchPersistent(ordered ? k_wf_shadow<true> : k_wf_shadow<false>, W, numSMs, stream);
+    if (W.sharedLoop) launchPersistent(ordered ? k_wf_shadow<true, true> : k_wf_shadow<false, true>, W, numSMs, stream);
+    else launchPersistent(ordered ? k_wf_shadow<true, false> : k_wf_shadow<false, false>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;
     if (W.dense) { k_wf_resolve<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
