@@ -129,7 +129,7 @@ typedef struct yahr_scene_info {
   double build_ms;          /* host BVH construction (restating Culling.hs:27-112) */
   double upload_ms;
   uint32_t built_on_device; /* 1: BVH built by the GPU builder, 0: host builder */
-  uint32_t reserved0;
+  uint32_t n_wide_nodes;    /* 4-wide collapse of the tree used by the traversal kernels (0: not built) */
 } yahr_scene_info;
 
 typedef struct yahr_scene yahr_scene;
@@ -150,6 +150,9 @@ int yahr_b200_scene_info(const yahr_scene* scene, yahr_scene_info* out);
  * uint32 (first, count).  Any output may be NULL. */
 int yahr_b200_scene_download_bvh(const yahr_scene* scene, uint32_t* order_out, float* nodes_out, uint32_t* multi_out,
                                  uint32_t* root_ref_out, float root_box_out[6]);
+/* Inspection: the 4-wide collapse of that tree the traversal kernels walk (yahr_scene_info.n_wide_nodes x 32
+ * floats; layout in csrc/device_types.cuh). */
+int yahr_b200_scene_download_wide(const yahr_scene* scene, float* wide_out);
 
 /* --- render: replaces render / renderEval / renderPar + samplesToImage (main.hs:68-107) -------- */
 /* Host-buffer entry (the call the Haskell host makes).  rgb_out: W*H*3 floats, row-major, RGB

@@ -56,8 +56,16 @@ def gpu_render_modes(sc, cam, depth=1, spp=1, seed=0):
                                   seed=seed, traversal=mode, stream=torch.cuda.current_stream().cuda_stream,
                                   kernel=kernel)
             outs[kname + "/" + name] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
+    if depth == 1:
+        # tuning bit 10: the wavefront set on the BINARY tree (default: its 4-wide collapse, wide_bvh.cu)
+        d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
+        d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
+        st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
+                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x400)
+        outs["wavefront/binary"] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
     outs["reference"] = outs["mega/reference"]
     outs["ordered"] = outs["mega/ordered"]
+    outs["info"] = s.info()
     s.close()
     return outs
 
@@ -92,7 +100,7 @@ def test_parity_small_scenes(name):
     orgb, opid, _, ost = o.render(cam)
     o.close()
     outs = gpu_render_modes(sc, cam)
-    for mode in ("host", "mega/reference", "wavefront/reference"):
+    for mode in ("host", "mega/reference", "wavefront/reference", "wavefront/binary"):
         rgb, pid, st = outs[mode]
         compare(rgb, pid, orgb, opid, 1.0, "%s/%s" % (name, mode))
         assert st["n_primary"] == ost["n_primary"]
@@ -105,10 +113,80 @@ def test_parity_small_scenes(name):
     # kernel sets agree bit for bit on IDs (radiance: same arithmetic, so bit-equal as well)
     assert np.array_equal(outs["host"][1], outs["wavefront/reference"][1])
     assert np.array_equal(outs["mega/reference"][1], outs["wavefront/reference"][1])
-    a, b = outs["mega/reference"][0], outs["wavefront/reference"][0]
-    nan = np.isnan(a) | np.isnan(b)
-    assert np.array_equal(np.isnan(a), np.isnan(b))
-    assert np.array_equal(np.where(nan, 0, a), np.where(nan, 0, b))
+    for other in ("wavefront/reference", "wavefront/binary"):
+        a, b = outs["mega/reference"][0], outs[other][0]
+        nan = np.isnan(a) | np.isnan(b)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(np.where(nan, 0, a), np.where(nan, 0, b))
+    if outs["info"]["n_nodes"] > 0:
+        assert outs["info"]["n_wide_nodes"] > 0, "the 4-wide tree was not built"
+
+
+def _wide_leaf_sequence(wide, root_ref):
+    """Leaf refs of the 4-wide tree in left-first order + (ref -> box) of every child slot."""
+    refs = wide[:, 24:28].view(np.uint32)
+    seq, boxes = [], {}
+    stack = [("n", root_ref)]
+    while stack:
+        _, ref = stack.pop()
+        if ref & 0x80000000:
+            seq.append(int(ref))
+            continue
+        node = wide[ref]
+        n = int(node[28:29].view(np.uint32)[0])
+        assert 2 <= n <= 4
+        kids = []
+        for k in range(4):
+            r = int(refs[ref, k])
+            if k >= n:
+                assert r == 0xFFFFFFFF and node[4 * k] == np.inf and node[4 * k + 2] == -np.inf
+                continue
+            lo = (node[4 * k], node[4 * k + 1], node[16 + 2 * k])
+            hi = (node[4 * k + 2], node[4 * k + 3], node[16 + 2 * k + 1])
+            if r & 0x80000000:
+                boxes[r] = lo + hi
+            kids.append(r)
+        for r in reversed(kids):
+            stack.append(("n", r))
+    return seq, boxes
+
+
+def _binary_leaf_sequence(nodes, root_ref):
+    refs = nodes[:, 12:14].view(np.uint32)
+    seq, boxes = [], {}
+    stack = [root_ref]
+    while stack:
+        ref = stack.pop()
+        if ref & 0x80000000:
+            seq.append(int(ref))
+            continue
+        nd = nodes[ref]
+        l, r = int(refs[ref, 0]), int(refs[ref, 1])
+        if l & 0x80000000:
+            boxes[l] = (nd[0], nd[1], nd[8], nd[2], nd[3], nd[9])
+        if r & 0x80000000:
+            boxes[r] = (nd[4], nd[5], nd[10], nd[6], nd[7], nd[11])
+        stack.append(r)
+        stack.append(l)
+    return seq, boxes
+
+
+@pytest.mark.parametrize("name", ["terrain", "grid-sah", "bunny-depth6", "soup"])
+def test_wide_tree_is_a_collapse_of_the_reference_tree(name):
+    """The 4-wide tree must present the same leaves, in the same left-first order, with the same leaf boxes
+    as the binary tree restating Culling.hs -- that is all the traversal result depends on (wide_bvh.cu)."""
+    sc, cam = SMALL[name]()
+    s = api.Scene(sc)
+    _, nodes, _, root, _ = s.download_bvh()
+    wide = s.download_wide()
+    s.close()
+    assert len(wide) > 0 and len(wide) < len(nodes)
+    bseq, bbox = _binary_leaf_sequence(nodes, root)
+    wseq, wbox = _wide_leaf_sequence(wide, root)
+    assert bseq == wseq
+    assert set(bbox) == set(wbox)
+    for r in bbox:
+        assert tuple(map(float, bbox[r])) == tuple(map(float, wbox[r]))
 
 
 @pytest.mark.parametrize("depth", [0, 2, 3])

@@ -68,7 +68,7 @@ class Stats(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_primitives", C.c_uint32), ("n_nodes", C.c_uint32), ("n_multi_leaves", C.c_uint32),
                 ("depth", C.c_uint32), ("device_bytes", C.c_uint64), ("build_ms", C.c_double),
-                ("upload_ms", C.c_double), ("built_on_device", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("upload_ms", C.c_double), ("built_on_device", C.c_uint32), ("n_wide_nodes", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -268,6 +268,16 @@ class Scene:
         _check(L.yahr_b200_scene_download_bvh(self._h, order.ctypes.data, nodes.ctypes.data, multi.ctypes.data,
                                               C.byref(root), box.ctypes.data))
         return order, nodes, multi, root.value, box
+
+    def download_wide(self):
+        """wide[n_wide_nodes, 32] float32 raw: the 4-wide collapse of the tree (csrc/device_types.cuh)."""
+        i = self.info()
+        wide = np.zeros((i["n_wide_nodes"], 32), np.float32)
+        L = lib()
+        L.yahr_b200_scene_download_wide.restype = C.c_int
+        L.yahr_b200_scene_download_wide.argtypes = [C.c_void_p, C.c_void_p]
+        _check(L.yahr_b200_scene_download_wide(self._h, wide.ctypes.data))
+        return wide
 
     def render_rgb8(self, cam, recursion_depth=1, spp=1, seed=0, out=None):
         """yahr_b200_render_rgb8: the frame with the reference's 8-bit output stage applied on the GPU."""

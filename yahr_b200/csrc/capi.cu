@@ -18,6 +18,7 @@
 #include "device_types.cuh"
 #include "host_scene.hpp"
 #include "kernels.hpp"
+#include "wide_bvh.hpp"
 #include "yahrr_parser.hpp"
 
 using namespace yb;
@@ -76,6 +77,7 @@ struct yahr_scene {
   int device = 0;
   DeviceScene dev{};
   float4* d_nodes = nullptr;
+  float4* d_wide = nullptr;              // 4-wide collapse of d_nodes (NULL: the root is a leaf, or not built)
   float4* d_prims = nullptr;
   float4* d_normals = nullptr;
   uint2* d_multi = nullptr;
@@ -106,7 +108,7 @@ struct yahr_scene {
   std::vector<cudaEvent_t> bandEvents;
 
   ~yahr_scene() {
-    cudaFree(d_nodes); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
+    cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
@@ -225,13 +227,13 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.base = P;
     W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
-    const uint32_t tune = (uint32_t)opts->reserved[0];
+    static const uint32_t envTune = getenv("YAHR_B200_TUNE") ? (uint32_t)strtoul(getenv("YAHR_B200_TUNE"), nullptr, 0) : 0u;
+    const uint32_t tune = opts->reserved[0] ? (uint32_t)opts->reserved[0] : envTune;
     W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 4u;
     W.blocksPerSM = (tune >> 16) & 0xFF;
     W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
-    W.sharedLoop = (tune >> 10) & 1u;              // default: nine specialised loops (bit 10 set = one shared loop;
-                                                   // measured slower: the per-step switch costs more than the I-cache saves)
+    W.wideTree = ((tune >> 10) & 1u) ^ 1u;         // default: 4-wide tree (bit 10 set = binary tree)
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
   }
   return YAHR_OK;
@@ -307,6 +309,24 @@ int renderCommon(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts*
     CU(cudaStreamSynchronize(stream));
   }
   return YAHR_OK;
+}
+
+// Collapses the device-resident binary tree into 4-wide nodes (wide_bvh.cu); shared by both build paths.
+// A tree whose wide walk could outgrow the traversal stack keeps the binary walk only.
+void attachWideTree(yahr_scene* sc) {
+  if (getenv("YAHR_B200_NO_WIDE") || !sc->d_nodes || sc->info.n_nodes == 0) return;
+  const double t0 = nowMs();
+  WideBuildOutput wo;
+  if (!buildWideOnDevice(sc->d_nodes, sc->info.n_nodes, sc->info.depth, wo)) throw CudaFailure{wo.error, wo.where, __FILE__, __LINE__};
+  if (wo.wide && wo.stackNeed < (uint32_t)YAHR_B200_MAX_STACK) {   // one scratch slot past the top (wideStep)
+    sc->d_wide = wo.wide;
+    sc->dev.wide = wo.wide;
+    sc->info.n_wide_nodes = wo.nWide;
+    sc->info.device_bytes += (uint64_t)wo.nWide * kWideNodeVec * sizeof(float4);
+  } else {
+    cudaFree(wo.wide);
+  }
+  sc->info.build_ms += nowMs() - t0;
 }
 
 // Small per-scene tables (materials, lights), events, counters: shared by both build paths.
@@ -409,6 +429,7 @@ int createSceneOnDevice(const yahr_scene_desc* d, yahr_scene** out) {
     sc->info.depth = bo.depth; sc->info.device_bytes = bytes;
     sc->info.build_ms = t2 - t1; sc->info.upload_ms = t1 - t0;
     sc->info.built_on_device = 1;
+    attachWideTree(sc);
     CU(cudaDeviceSynchronize());
     *out = sc;
     return YAHR_OK;
@@ -539,6 +560,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     sc->info.build_ms = t1 - t0;
     sc->info.upload_ms = t3 - t2;
     sc->info.built_on_device = 0;
+    attachWideTree(sc);
     *out = sc;
     return YAHR_OK;
   } catch (const CudaFailure& f) {
@@ -578,6 +600,18 @@ int yahr_b200_scene_download_bvh(const yahr_scene* scene, uint32_t* order_out, f
     if (root_ref_out) *root_ref_out = scene->dev.rootRef;
     if (root_box_out)
       for (int c = 0; c < 3; ++c) { root_box_out[c] = scene->dev.rootLo[c]; root_box_out[3 + c] = scene->dev.rootHi[c]; }
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  }
+}
+
+int yahr_b200_scene_download_wide(const yahr_scene* scene, float* wide_out) {
+  if (!scene || !wide_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  try {
+    if (scene->info.n_wide_nodes)
+      CU(cudaMemcpy(wide_out, scene->d_wide, (size_t)scene->info.n_wide_nodes * kWideNodeVec * sizeof(float4),
+                    cudaMemcpyDeviceToHost));
     return YAHR_OK;
   } catch (const CudaFailure& f) {
     return cudaFail(f);

@@ -18,11 +18,17 @@ namespace yb {
 //               (Shapes.hs:38-39) done once on the host in binary32.
 //   normals   : 3 x float4 per primitive (n0, n1, n2), same order; only read for triangle
 //               candidates that pass the barycentric / t tests                                 48 B
+//   wide      : 8 x float4 per 4-wide node (collapse of the binary tree, wide_bvh.cu)           128 B
+//                 child k = 0..3: (lo.x lo.y hi.x hi.y); then (z of child 0, 1) (z of child 2, 3) as
+//                 (lo.z hi.z lo.z hi.z); then the four child refs; then (child count, binary root, -, -).
+//               Inner refs index `wide`; leaf refs are the binary tree's.  Empty slots hold the box
+//               (+inf, -inf) and the null ref.  Used by rays whose 1/u components are all finite.
 //   multiLeaves : (first, count) per multi-leaf
 //   materials : 2 x float4 = (diffuse.rgb, shininess), (specular.rgb, 0)
 //   lights    : 2 x float4 = (position.xyz, 0), (spectrum.rgb, 0)
 struct DeviceScene {
   const float4* nodes;
+  const float4* wide;
   const float4* prims;
   const float4* normals;
   const uint2* multiLeaves;
@@ -36,6 +42,8 @@ struct DeviceScene {
 static const uint32_t kDevRefNull = 0xFFFFFFFFu;
 static const uint32_t kDevRefLeafBit = 0x80000000u;
 static const uint32_t kDevRefMultiBits = 0xC0000000u;
+static const int kWideWidth = 4;          // children per wide node
+static const int kWideNodeVec = 8;        // float4 per wide node
 
 struct RenderParams {
   DeviceScene sc;
@@ -66,7 +74,7 @@ struct WavefrontParams {
   uint32_t blocksPerSM;       // tuning: persistent CTAs per SM (0 = as many as fit)
   uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
-  uint32_t sharedLoop;        // one traversal loop with a switch on the octant (smaller code) vs nine loops
+  uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)

@@ -172,10 +172,9 @@ __device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray
 
 // Picks the octant-specialised walk when every busy lane of the warp shares one octant and no lane
 // can produce NaN slab products; otherwise the generic walk.
-template <bool ANY_HIT, bool ORDERED, bool SHARED>
+template <bool ANY_HIT, bool ORDERED>
 __device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
                                              int leafThreshold, bool packed) {
-  constexpr bool sharedLoop = SHARED;
   const unsigned mBusy = __ballot_sync(kFull, busy);
   if (mBusy == 0) return;
   int oct = -1;
@@ -183,35 +182,6 @@ __device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r
     const int mine = rayOctant(r);
     const int lead = __shfl_sync(kFull, mine, __ffs(mBusy) - 1);
     if (__all_sync(kFull, !busy || (mine == lead && !r.exactNaN))) oct = lead;
-  }
-  if (sharedLoop) {
-    // one loop, one copy of the leaf code; only the node step is specialised (the octant is warp-uniform,
-    // so the switch is a uniform branch).  Keeps the kernel small enough for the instruction cache.
-    const RayPack rp = packRay(r);
-    for (;;) {
-      const bool atLeaf = busy && (s.cur & kDevRefLeafBit);
-      const bool atInner = busy && !atLeaf;
-      const unsigned mLeaf = __ballot_sync(kFull, atLeaf);
-      const unsigned mInner = __ballot_sync(kFull, atInner);
-      if ((mLeaf | mInner) == 0) break;
-      if (mInner == 0 || __popc(mLeaf) >= leafThreshold) {
-        if (atLeaf) busy = leafStep<ANY_HIT, ORDERED>(sc, r, s, stack);
-      }
-      if (atInner) {
-        switch (oct) {
-          case 0: busy = innerStep<ORDERED, 0>(sc, r, rp, s, stack); break;
-          case 1: busy = innerStep<ORDERED, 1>(sc, r, rp, s, stack); break;
-          case 2: busy = innerStep<ORDERED, 2>(sc, r, rp, s, stack); break;
-          case 3: busy = innerStep<ORDERED, 3>(sc, r, rp, s, stack); break;
-          case 4: busy = innerStep<ORDERED, 4>(sc, r, rp, s, stack); break;
-          case 5: busy = innerStep<ORDERED, 5>(sc, r, rp, s, stack); break;
-          case 6: busy = innerStep<ORDERED, 6>(sc, r, rp, s, stack); break;
-          case 7: busy = innerStep<ORDERED, 7>(sc, r, rp, s, stack); break;
-          default: busy = innerStep<ORDERED, -1>(sc, r, rp, s, stack); break;
-        }
-      }
-    }
-    return;
   }
   switch (oct) {
     case 0: traverseWarpOct<ANY_HIT, ORDERED, 0>(sc, r, s, stack, busy, leafThreshold); break;
@@ -224,6 +194,111 @@ __device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r
     case 7: traverseWarpOct<ANY_HIT, ORDERED, 7>(sc, r, s, stack, busy, leafThreshold); break;
     default: traverseWarpOct<ANY_HIT, ORDERED, -1>(sc, r, s, stack, busy, leafThreshold); break;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-wide traversal (wide_bvh.cu): same leaves, same order, same tMax at every leaf as the binary walk
+// for every ray whose 1/u components are finite; the others (NaN slab products) use the binary tree.
+// ---------------------------------------------------------------------------------------------
+
+// Slab test of one child box of a wide node.  OCT as in childTestsOct; OCT = -1 takes min / max per lane.
+template <int OCT>
+__device__ __forceinline__ void wideChildTest(const float4& b, float zlo, float zhi, const RayPack& p, float tMax,
+                                              bool& pass, float& key) {
+  const float2 lo = __fmul2_rn(__fadd2_rn(make_float2(b.x, b.y), p.negOxy), p.invXy);   // t0x t0y
+  const float2 hi = __fmul2_rn(__fadd2_rn(make_float2(b.z, b.w), p.negOxy), p.invXy);   // t1x t1y
+  const float2 zz = __fmul2_rn(__fadd2_rn(make_float2(zlo, zhi), p.negOzz), p.invZz);   // t0z t1z
+  float tN, tF;
+  if (OCT >= 0) {
+    constexpr bool NX = (OCT & 1) != 0, NY = (OCT & 2) != 0, NZ = (OCT & 4) != 0;
+    tN = fmaxf(fmaxf(fmaxf(0.0f, NX ? hi.x : lo.x), NY ? hi.y : lo.y), NZ ? zz.y : zz.x);
+    tF = fminf(fminf(fminf(tMax, NX ? lo.x : hi.x), NY ? lo.y : hi.y), NZ ? zz.x : zz.y);
+  } else {
+    tN = fmaxf(fmaxf(fmaxf(0.0f, fminf(lo.x, hi.x)), fminf(lo.y, hi.y)), fminf(zz.x, zz.y));
+    tF = fminf(fminf(fminf(tMax, fmaxf(lo.x, hi.x)), fmaxf(lo.y, hi.y)), fmaxf(zz.x, zz.y));
+  }
+  key = tN;
+  pass = tN <= tF;
+}
+
+// One wide-node visit: four child box tests; the first passing child (left-first order) is entered, the
+// later passing ones are pushed in reverse order with their entry distance (re-validated against the then
+// current tMax when popped, exactly like the binary walk).  Returns false when the walk is finished.
+template <int OCT>
+__device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& rp, Trav& s, uint2* stack) {
+  const float4* np = sc.wide + kWideNodeVec * (size_t)s.cur;
+  const float4 b0 = __ldg(np + 0), b1 = __ldg(np + 1), b2 = __ldg(np + 2), b3 = __ldg(np + 3);
+  const float4 z01 = __ldg(np + 4), z23 = __ldg(np + 5), rf = __ldg(np + 6);
+  bool p0, p1, p2, p3;
+  float k0, k1, k2, k3;
+  wideChildTest<OCT>(b0, z01.x, z01.y, rp, s.tMax, p0, k0);
+  wideChildTest<OCT>(b1, z01.z, z01.w, rp, s.tMax, p1, k1);
+  wideChildTest<OCT>(b2, z23.x, z23.y, rp, s.tMax, p2, k2);
+  wideChildTest<OCT>(b3, z23.z, z23.w, rp, s.tMax, p3, k3);
+  const uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z),
+                 r3 = __float_as_uint(rf.w);
+  if (OCT < 0) {       // per-lane min / max cannot tell the inverted box of an empty slot from a real one
+    p0 = p0 && r0 != kDevRefNull; p1 = p1 && r1 != kDevRefNull; p2 = p2 && r2 != kDevRefNull; p3 = p3 && r3 != kDevRefNull;
+  }
+  // branch-free push: a later child goes on the stack iff it passes and an earlier one does too; the stores
+  // are unconditional (one slot past the top is scratch), only the stack pointer moves conditionally
+  int sp = s.sp;
+  stack[sp] = make_uint2(r3, __float_as_uint(k3)); sp += (p3 && (p0 || p1 || p2)) ? 1 : 0;
+  stack[sp] = make_uint2(r2, __float_as_uint(k2)); sp += (p2 && (p0 || p1)) ? 1 : 0;
+  stack[sp] = make_uint2(r1, __float_as_uint(k1)); sp += (p1 && p0) ? 1 : 0;
+  s.sp = sp;
+  if (p0 || p1 || p2 || p3) {
+    s.cur = p0 ? r0 : (p1 ? r1 : (p2 ? r2 : r3));
+    return true;
+  }
+  return popNext(s, stack);
+}
+
+// Inner phase of the wide walk: wide-node steps until no lane has inner work or enough lanes hold a leaf.
+// Only this loop is specialised per octant; the leaf code exists once (traverseWarpWide).
+template <int OCT>
+__device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& rp, Trav& s, uint2* stack, bool& run,
+                                          int leafThreshold) {
+  for (;;) {
+    const bool atLeaf = run && (s.cur & kDevRefLeafBit);
+    const bool atInner = run && !atLeaf;
+    if (!__any_sync(kFull, atInner)) break;
+    if (__popc(__ballot_sync(kFull, atLeaf)) >= leafThreshold) break;
+    if (atInner) run = wideStep<OCT>(sc, rp, s, stack);
+  }
+}
+
+template <bool ANY_HIT>
+__device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+                                                 int leafThreshold) {
+  const bool nanLane = busy && r.exactNaN;
+  bool run = busy && !r.exactNaN;
+  const unsigned mRun = __ballot_sync(kFull, run);
+  if (mRun) {
+    int oct = -1;
+    const int mine = rayOctant(r);
+    const int lead = __shfl_sync(kFull, mine, __ffs(mRun) - 1);
+    if (__all_sync(kFull, !run || mine == lead)) oct = lead;
+    const RayPack rp = packRay(r);
+    for (;;) {
+      switch (oct) {
+        case 0: widePhase<0>(sc, rp, s, stack, run, leafThreshold); break;
+        case 1: widePhase<1>(sc, rp, s, stack, run, leafThreshold); break;
+        case 2: widePhase<2>(sc, rp, s, stack, run, leafThreshold); break;
+        case 3: widePhase<3>(sc, rp, s, stack, run, leafThreshold); break;
+        case 4: widePhase<4>(sc, rp, s, stack, run, leafThreshold); break;
+        case 5: widePhase<5>(sc, rp, s, stack, run, leafThreshold); break;
+        case 6: widePhase<6>(sc, rp, s, stack, run, leafThreshold); break;
+        case 7: widePhase<7>(sc, rp, s, stack, run, leafThreshold); break;
+        default: widePhase<-1>(sc, rp, s, stack, run, leafThreshold); break;
+      }
+      // every running lane now holds a leaf, or enough of them do
+      const bool atLeaf = run && (s.cur & kDevRefLeafBit);
+      if (!__any_sync(kFull, atLeaf)) break;
+      if (atLeaf) run = leafStep<ANY_HIT, false>(sc, r, s, stack);
+    }
+  }
+  if (__any_sync(kFull, nanLane)) traverseWarpOct<ANY_HIT, false, -1>(sc, r, s, stack, nanLane, 1);
 }
 
 // item index (tile-major) -> tile.  Tiles are almost uniform in size, so a proportional guess is
@@ -353,7 +428,7 @@ __device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, int MIN_BLOCKS, bool SHARED>
+template <bool ORDERED, int MIN_BLOCKS, bool WIDE>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
@@ -376,13 +451,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
-    traverseWarp<false, ORDERED, SHARED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold);
+    else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     shadeAndEmit(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, bool SHARED>
+template <bool ORDERED, bool WIDE>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
@@ -407,7 +483,8 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ Wavef
         busy = travBegin(W.base.sc, r, a.w, s);
       }
     }
-    traverseWarp<true, ORDERED, SHARED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold);
+    else traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     if (probe) shadowResult(W, entry, s.best == kNoHit);
   }
 }
@@ -476,17 +553,16 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     W.sampleOut = W.base.spp == 1 ? W.base.rgb : W.sampleBuf;
     const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
     if (timed) cudaEventRecord(phaseEvents[0], stream);
-    if (W.sharedLoop)
-      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, true> : k_wf_primary<false, 8, true>)
-                                      : (ordered ? k_wf_primary<true, 1, true> : k_wf_primary<false, 1, true>),
-                       W, numSMs, stream);
+    const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
+    if (wide)
+      launchPersistent(W.capRegisters ? k_wf_primary<false, 8, true> : k_wf_primary<false, 1, true>, W, numSMs, stream);
     else
       launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false> : k_wf_primary<false, 8, false>)
                                       : (ordered ? k_wf_primary<true, 1, false> : k_wf_primary<false, 1, false>),
                        W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
-    if (W.sharedLoop) launchPersistent(ordered ? k_wf_shadow<true, true> : k_wf_shadow<false, true>, W, numSMs, stream);
+    if (wide) launchPersistent(k_wf_shadow<false, true>, W, numSMs, stream);
     else launchPersistent(ordered ? k_wf_shadow<true, false> : k_wf_shadow<false, false>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;

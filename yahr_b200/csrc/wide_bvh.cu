@@ -1,0 +1,189 @@
+// wide_bvh.cu -- collapses the reference's binary BVH (64-byte nodes, pre-order) into 4-wide nodes ON THE GPU.
+//
+// Why this keeps primitive IDs bit-exact.  In the reference a subtree is entered iff its box test passes with
+// the ray's CURRENT tMax (wrapCollider, AABBs.hs:42-43; Culling.hs:24-25,33,38,52).  A parent's box is the
+// `join` of its children's boxes (Culling.hs:39; min / max are exact), so every child box is contained in the
+// parent box, and for a ray whose 1/u components are all finite the slab arithmetic (b - o) * (1/u) is monotone
+// in b: the child's [tNear, tFar] interval lies inside the parent's.  Hence "child passes with tMax'" implies
+// "parent passes with any tMax >= tMax'", and since tMax only shrinks during a walk:
+//     a node is entered by the reference  <=>  its OWN box passes with the tMax current at that moment.
+// The boxes of the ancestors are redundant; any hierarchy over the same leaf sequence (same left-first order,
+// same leaf boxes) visits exactly the same leaves with exactly the same tMax values.  A wide node simply holds
+// the boxes of up to four descendants of one binary node, in left-first order, and skips the boxes in between.
+// Rays with a non-finite 1/u component (NaN slab products, SURVEY.md note N) are not monotone and keep using the
+// binary tree.
+//
+//   k_wide_mark  : waves from the root; a marked binary node becomes a wide node, its expansion (below) names
+//                  the binary nodes that become its wide children -> marked in the next wave
+//   scan         : wide index = rank of the marked node in pre-order (keeps the left child adjacent)
+//   k_wide_emit  : one thread per marked node writes the 128-byte wide node
+//
+// Expansion of binary node i: start with its two children; while fewer than four slots, replace the INNER slot
+// with the largest surface area by its two children (in place, so the slots stay in left-first order).
+#include "wide_bvh.hpp"
+
+#include <cub/cub.cuh>
+
+namespace yb {
+namespace {
+
+struct Slot {
+  uint32_t ref;
+  float lox, loy, hix, hiy, loz, hiz;
+};
+
+__device__ __forceinline__ void loadChildren(const float4* flat, uint32_t i, Slot& a, Slot& b) {
+  const float4 n0 = flat[4 * (size_t)i + 0], n1 = flat[4 * (size_t)i + 1], n2 = flat[4 * (size_t)i + 2],
+               n3 = flat[4 * (size_t)i + 3];
+  a.ref = __float_as_uint(n3.x); a.lox = n0.x; a.loy = n0.y; a.hix = n0.z; a.hiy = n0.w; a.loz = n2.x; a.hiz = n2.y;
+  b.ref = __float_as_uint(n3.y); b.lox = n1.x; b.loy = n1.y; b.hix = n1.z; b.hiy = n1.w; b.loz = n2.z; b.hiz = n2.w;
+}
+
+__device__ __forceinline__ bool isInner(uint32_t ref) { return (ref & kDevRefLeafBit) == 0; }   // null has the bit set
+
+__device__ __forceinline__ float slotArea(const Slot& s) {
+  const float dx = s.hix - s.lox, dy = s.hiy - s.loy, dz = s.hiz - s.loz;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// The slots of the wide node rooted at binary node i, in left-first order.  Deterministic: the mark and the
+// emit pass must agree.
+__device__ int expandNode(const float4* flat, uint32_t i, Slot s[kWideWidth]) {
+  int n = 2;
+  loadChildren(flat, i, s[0], s[1]);
+  while (n < kWideWidth) {
+    int best = -1;
+    float bestA = 0.0f;
+    for (int k = 0; k < n; ++k) {
+      if (!isInner(s[k].ref)) continue;
+      const float a = slotArea(s[k]);
+      if (best < 0 || a > bestA) { best = k; bestA = a; }
+    }
+    if (best < 0) break;
+    for (int k = n; k > best + 1; --k) s[k] = s[k - 1];
+    Slot l, r;
+    loadChildren(flat, s[best].ref, l, r);
+    s[best] = l;
+    s[best + 1] = r;
+    ++n;
+  }
+  return n;
+}
+
+__global__ void k_wide_mark(const float4* flat, uint32_t nInner, uint32_t* mark, uint32_t wave) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nInner || mark[i] != wave) return;
+  Slot s[kWideWidth];
+  const int n = expandNode(flat, i, s);
+  for (int k = 0; k < n; ++k)
+    if (isInner(s[k].ref)) mark[s[k].ref] = wave + 1u;
+}
+
+__global__ void k_wide_flags(const uint32_t* mark, uint32_t nInner, uint32_t* flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nInner) flags[i] = (i < nInner && mark[i] != 0u) ? 1u : 0u;
+}
+
+__global__ void k_wide_emit(const float4* flat, uint32_t nInner, const uint32_t* mark, const uint32_t* wideIdx,
+                            float4* wide) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nInner || mark[i] == 0u) return;
+  Slot s[kWideWidth];
+  const int n = expandNode(flat, i, s);
+  float4* out = wide + kWideNodeVec * (size_t)wideIdx[i];
+  uint32_t refs[kWideWidth];
+  float z[2 * kWideWidth];
+  for (int k = 0; k < kWideWidth; ++k) {
+    if (k < n) {
+      out[k] = make_float4(s[k].lox, s[k].loy, s[k].hix, s[k].hiy);
+      z[2 * k] = s[k].loz; z[2 * k + 1] = s[k].hiz;
+      refs[k] = isInner(s[k].ref) ? wideIdx[s[k].ref] : s[k].ref;
+    } else {
+      // empty slot: an inverted infinite box fails the slab test of every ray with finite 1/u
+      out[k] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+      z[2 * k] = INFINITY; z[2 * k + 1] = -INFINITY;
+      refs[k] = kDevRefNull;
+    }
+  }
+  out[4] = make_float4(z[0], z[1], z[2], z[3]);
+  out[5] = make_float4(z[4], z[5], z[6], z[7]);
+  out[6] = make_float4(__uint_as_float(refs[0]), __uint_as_float(refs[1]), __uint_as_float(refs[2]),
+                       __uint_as_float(refs[3]));
+  out[7] = make_float4(__uint_as_float((uint32_t)n), __uint_as_float(i), 0.0f, 0.0f);     // inspection only
+}
+
+// Deepest traversal stack the wide walk can need below a wide node: when child k is entered, at most the
+// n - 1 - k later children are on the stack.  Runs bottom-up: children carry a later wave number.
+__global__ void k_wide_need(const float4* wide, uint32_t nInner, const uint32_t* mark, const uint32_t* wideIdx,
+                            uint32_t wave, uint32_t* need) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nInner || mark[i] != wave) return;
+  const uint32_t w = wideIdx[i];
+  const float4 rf = wide[kWideNodeVec * (size_t)w + 6];
+  const uint32_t n = __float_as_uint(wide[kWideNodeVec * (size_t)w + 7].x);
+  const uint32_t refs[4] = {__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w)};
+  uint32_t m = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t below = isInner(refs[k]) ? need[refs[k]] : 0u;
+    m = max(m, (n - 1u - k) + below);
+  }
+  need[w] = m;
+}
+
+inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+#define WB(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      out.error = e__; out.where = #call;                                                   \
+      cudaFree(mark); cudaFree(flags); cudaFree(scan); cudaFree(temp); cudaFree(need);      \
+      cudaFree(out.wide);                                                                   \
+      out.wide = nullptr;                                                                   \
+      return false;                                                                         \
+    }                                                                                       \
+  } while (0)
+
+bool buildWideOnDevice(const float4* flat, uint32_t nInner, uint32_t binaryDepth, WideBuildOutput& out) {
+  out = WideBuildOutput();
+  if (nInner == 0 || !flat) return true;              // the root is a leaf (or the scene is empty): nothing to collapse
+  uint32_t *mark = nullptr, *flags = nullptr, *scan = nullptr, *need = nullptr;
+  void* temp = nullptr;
+  size_t tempBytes = 0;
+  cudaStream_t st = nullptr;
+  WB(cudaMalloc(&mark, (size_t)nInner * sizeof(uint32_t)));
+  WB(cudaMalloc(&flags, ((size_t)nInner + 1) * sizeof(uint32_t)));
+  WB(cudaMalloc(&scan, ((size_t)nInner + 1) * sizeof(uint32_t)));
+  WB(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, flags, scan, (int)(nInner + 1), st));
+  WB(cudaMalloc(&temp, tempBytes ? tempBytes : 1));
+  WB(cudaMemsetAsync(mark, 0, (size_t)nInner * sizeof(uint32_t), st));
+  const uint32_t one = 1u;
+  WB(cudaMemcpyAsync(mark, &one, sizeof(one), cudaMemcpyHostToDevice, st));     // the root (pre-order index 0)
+  // every wave descends at least one binary level, so binaryDepth + 1 waves reach every node
+  const uint32_t nWaves = binaryDepth + 2u;
+  for (uint32_t wave = 1; wave <= nWaves; ++wave)
+    k_wide_mark<<<blocks(nInner), 256, 0, st>>>(flat, nInner, mark, wave);
+  k_wide_flags<<<blocks((size_t)nInner + 1), 256, 0, st>>>(mark, nInner, flags);
+  WB(cub::DeviceScan::ExclusiveSum(temp, tempBytes, flags, scan, (int)(nInner + 1), st));
+  uint32_t nWide = 0;
+  WB(cudaMemcpyAsync(&nWide, scan + nInner, sizeof(nWide), cudaMemcpyDeviceToHost, st));
+  WB(cudaStreamSynchronize(st));
+  WB(cudaGetLastError());
+  WB(cudaMalloc(&out.wide, (size_t)(nWide ? nWide : 1) * kWideNodeVec * sizeof(float4)));
+  k_wide_emit<<<blocks(nInner), 256, 0, st>>>(flat, nInner, mark, scan, out.wide);
+  WB(cudaMalloc(&need, (size_t)(nWide ? nWide : 1) * sizeof(uint32_t)));
+  for (uint32_t wave = nWaves + 1u; wave >= 1u; --wave)
+    k_wide_need<<<blocks(nInner), 256, 0, st>>>(out.wide, nInner, mark, scan, wave, need);
+  uint32_t rootNeed = 0;
+  WB(cudaMemcpyAsync(&rootNeed, need, sizeof(rootNeed), cudaMemcpyDeviceToHost, st));
+  WB(cudaStreamSynchronize(st));
+  WB(cudaGetLastError());
+  out.nWide = nWide;
+  out.stackNeed = rootNeed;
+  cudaFree(mark); cudaFree(flags); cudaFree(scan); cudaFree(temp); cudaFree(need);
+  return true;
+}
+
+}  // namespace yb
