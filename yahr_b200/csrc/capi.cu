@@ -65,6 +65,7 @@ T* devUpload(const std::vector<T>& v, uint64_t& bytes) {
 struct TileSet {
   int4* d_tiles = nullptr;
   uint32_t* d_tileStart = nullptr;
+  uint32_t* d_itemPixels = nullptr;   // item -> (u | v << 16), built on the device when the set is created
   uint32_t n = 0, nItems = 0;
   std::vector<int4> hostTiles;        // windows, batch order (row-major over the tile grid)
   std::vector<uint32_t> hostStart;    // n + 1 prefix sums of the tile pixel counts
@@ -110,7 +111,7 @@ struct yahr_scene {
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
-    for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); }
+    for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); cudaFree(kv.second.d_itemPixels); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
     if (ev0) cudaEventDestroy(ev0);
@@ -162,6 +163,14 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
   uint64_t bytes = 0;
   ts.d_tiles = devUpload(host, bytes);
   ts.d_tileStart = devUpload(start, bytes);
+  if (ts.nItems && w <= 0xFFFF && h <= 0xFFFF && !getenv("YAHR_B200_NO_PIXEL_TABLE")) {
+    CU(cudaMalloc(&ts.d_itemPixels, (size_t)ts.nItems * sizeof(uint32_t)));
+    WavefrontParams T{};
+    T.base.tiles = ts.d_tiles; T.base.nTiles = ts.n; T.base.width = w; T.base.height = h;
+    T.tileStart = ts.d_tileStart; T.nItems = ts.nItems; T.itemBase = 0;
+    CU(launchPixelTable(T, ts.d_itemPixels, 0));
+    CU(cudaStreamSynchronize(0));
+  }
   return sc->tiles.emplace(key, ts).first->second;
 }
 
@@ -226,14 +235,16 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     }
     W.base = P;
     W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
+    W.itemPixels = ts.d_itemPixels;
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
     static const uint32_t envTune = getenv("YAHR_B200_TUNE") ? (uint32_t)strtoul(getenv("YAHR_B200_TUNE"), nullptr, 0) : 0u;
     const uint32_t tune = opts->reserved[0] ? (uint32_t)opts->reserved[0] : envTune;
-    W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 4u;
+    W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 12u;
     W.blocksPerSM = (tune >> 16) & 0xFF;
     W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
     W.wideTree = ((tune >> 10) & 1u) ^ 1u;         // default: 4-wide tree (bit 10 set = binary tree)
+    W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
   }
   return YAHR_OK;

@@ -68,6 +68,7 @@ struct WavefrontParams {
   const uint32_t* tileStart;  // nTiles + 1 prefix sums of the tile pixel counts
   uint32_t nItems;            // items of this launch (a range of tiles)
   uint32_t itemBase;          // tileStart value of the first tile of this launch
+  const uint32_t* itemPixels; // per item of the tile set (index item + itemBase): u | v << 16, or NULL (computed)
   uint32_t sample;            // sample index of this pass (spp > 1 runs one pass per sample)
   uint32_t dense;             // several lights: shadow slots entry = item * nLights + light
   uint32_t leafThreshold;     // leaf parking: run the leaf code once this many lanes hold a leaf
@@ -75,6 +76,7 @@ struct WavefrontParams {
   uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
+  uint32_t leafRun;           // wide walk: consecutive pending leaves of a lane are tested in one leaf phase
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)

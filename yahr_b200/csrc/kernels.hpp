@@ -16,6 +16,8 @@ cudaError_t launchQuantizeRgb8(const float* rgb, unsigned char* out, size_t firs
 namespace yb {
 // Persistent-thread wavefront kernel set (primary trace, shade, shadow trace, resolve); depth 1 only.
 // phaseEvents: NULL or 4 events recorded before primary / shade / shadow and after shadow (first sample).
+// Fills table[item] = u | v << 16 for every item of the tile set described by W (tiles, tileStart, nItems).
+cudaError_t launchPixelTable(WavefrontParams W, uint32_t* table, cudaStream_t stream);
 cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
                             cudaEvent_t* phaseEvents);
 }  // namespace yb

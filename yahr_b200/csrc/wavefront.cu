@@ -270,7 +270,7 @@ __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& 
 
 template <bool ANY_HIT>
 __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
-                                                 int leafThreshold) {
+                                                 int leafThreshold, bool leafRun) {
   const bool nanLane = busy && r.exactNaN;
   bool run = busy && !r.exactNaN;
   const unsigned mRun = __ballot_sync(kFull, run);
@@ -295,7 +295,10 @@ __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ra
       // every running lane now holds a leaf, or enough of them do
       const bool atLeaf = run && (s.cur & kDevRefLeafBit);
       if (!__any_sync(kFull, atLeaf)) break;
-      if (atLeaf) run = leafStep<ANY_HIT, false>(sc, r, s, stack);
+      // a lane whose next pending subtree is again a leaf (siblings in one wide node) tests it right away
+      if (atLeaf) {
+        do { run = leafStep<ANY_HIT, false>(sc, r, s, stack); } while (leafRun && run && (s.cur & kDevRefLeafBit));
+      }
     }
   }
   if (__any_sync(kFull, nanLane)) traverseWarpOct<ANY_HIT, false, -1>(sc, r, s, stack, nanLane, 1);
@@ -315,6 +318,11 @@ __device__ __forceinline__ uint32_t tileOfItem(const WavefrontParams& W, uint32_
 // 32 consecutive items (one warp) cover an 8 x 4 pixel block.  (The reference's own order inside a
 // tile, u-major (Sampling.hs:6), only matters for its list layout, not for the image.)
 __device__ __forceinline__ void itemPixel(const WavefrontParams& W, uint32_t item, int& u, int& v) {
+  if (W.itemPixels) {                      // precomputed once per tile set (k_wf_pixel_table): one coalesced load
+    const uint32_t p = __ldg(&W.itemPixels[item + W.itemBase]);
+    u = (int)(p & 0xFFFFu); v = (int)(p >> 16);
+    return;
+  }
   const uint32_t t = tileOfItem(W, item);
   const int4 win = __ldg(&W.base.tiles[t]);
   const int i = (int)(item + W.itemBase - __ldg(&W.tileStart[t]));
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
-    if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold);
+    if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     shadeAndEmit(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
   }
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ Wavef
         busy = travBegin(W.base.sc, r, a.w, s);
       }
     }
-    if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold);
+    if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     if (probe) shadowResult(W, entry, s.best == kNoHit);
   }
@@ -524,6 +532,22 @@ __global__ void __launch_bounds__(256) k_wf_accum(const __grid_constant__ Wavefr
     if ((int)W.sample == W.base.spp - 1) W.base.rgb[p + c] = __fdiv_rn(a, n);
     else W.accum[p + c] = a;
   }
+}
+
+// item -> pixel table of a tile set (built once, when the tile set is first used)
+__global__ void __launch_bounds__(256) k_wf_pixel_table(const __grid_constant__ WavefrontParams W, uint32_t* table) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= W.nItems) return;
+  int u, v;
+  itemPixel(W, item, u, v);
+  table[item + W.itemBase] = (uint32_t)u | ((uint32_t)v << 16);
+}
+
+cudaError_t launchPixelTable(WavefrontParams W, uint32_t* table, cudaStream_t stream) {
+  if (W.nItems == 0) return cudaSuccess;
+  W.itemPixels = nullptr;
+  k_wf_pixel_table<<<(W.nItems + 255u) / 256u, 256, 0, stream>>>(W, table);
+  return cudaGetLastError();
 }
 
 __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
