@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, bool WIDE>
-__global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
+template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t nEntries = W.dense ? W.nItems * W.base.sc.nLights : W.work[2];
@@ -586,8 +586,9 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
                        W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
-    if (wide) launchPersistent(k_wf_shadow<false, true>, W, numSMs, stream);
-    else launchPersistent(ordered ? k_wf_shadow<true, false> : k_wf_shadow<false, false>, W, numSMs, stream);
+    // 10 CTAs / SM (48 registers) measured 2-3 % faster than the unconstrained 56 registers / 9 CTAs
+    if (wide) launchPersistent(k_wf_shadow<false, true, 10>, W, numSMs, stream);
+    else launchPersistent(ordered ? k_wf_shadow<true, false, 1> : k_wf_shadow<false, false, 1>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;
     if (W.dense) { k_wf_resolve<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
