@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workloads", default="c4-terrain,c4-soup,c3,c2")
 ap.add_argument("--tunes", default="0,0x400")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between repetitions")
 args = ap.parse_args()
 api.build_library()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -32,7 +33,8 @@ for name in args.workloads.split(","):
         tune = int(t, 0)
         ms, ph = [], []
         for i in range(args.reps + 2):
-            flush.zero_()
+            if not args.no_flush:
+                flush.zero_()
             st = s.render_device(cam, rgb.data_ptr(), None, tune=tune, kernel=2)
             if i >= 2:
                 ms.append(st["gpu_ms"])

@@ -243,9 +243,13 @@ __device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& r
   // branch-free push: a later child goes on the stack iff it passes and an earlier one does too; the stores
   // are unconditional (one slot past the top is scratch), only the stack pointer moves conditionally
   int sp = s.sp;
-  stack[sp] = make_uint2(r3, __float_as_uint(k3)); sp += (p3 && (p0 || p1 || p2)) ? 1 : 0;
-  stack[sp] = make_uint2(r2, __float_as_uint(k2)); sp += (p2 && (p0 || p1)) ? 1 : 0;
-  stack[sp] = make_uint2(r1, __float_as_uint(k1)); sp += (p1 && p0) ? 1 : 0;
+  const bool e3 = p3 && (p0 || p1 || p2), e2 = p2 && (p0 || p1), e1 = p1 && p0;
+  if (e3) stack[sp] = make_uint2(r3, __float_as_uint(k3));
+  sp += e3 ? 1 : 0;
+  if (e2) stack[sp] = make_uint2(r2, __float_as_uint(k2));
+  sp += e2 ? 1 : 0;
+  if (e1) stack[sp] = make_uint2(r1, __float_as_uint(k1));
+  sp += e1 ? 1 : 0;
   s.sp = sp;
   if (p0 || p1 || p2 || p3) {
     s.cur = p0 ? r0 : (p1 ? r1 : (p2 ? r2 : r3));
