@@ -40,16 +40,41 @@ def _load_bytes_per_ray():
         return {}
 
 
-# smsp__issue_active (fraction of issue slots used) and threads per instruction of the dominant kernels
-ISSUE_UTIL = {("c4-terrain", "mega"): {"k_render_mega": 0.50, "active_threads_per_inst": 17.96,
-                                       "source": "profiles/r1a_ncu_full_k_render_mega_c4terrain.txt"},
-              ("c4-terrain", "wavefront"): {"k_wf_primary": 0.69, "k_wf_shadow": 0.80, "active_threads_per_inst": 22.3,
-                                            "source": "profiles/r1h_ncu_full_wavefront_c4terrain.txt"}}
+# Figures taken from the committed `ncu --set full` captures (profiles/*.json written by tools/ncu_summary.py from
+# the .ncu-rep of this same command): DRAM bytes per frame and what actually bounds the kernels.
+NCU_SUMMARIES = {("c4-terrain", "wavefront"): "profiles/r1r_ncu_full_wavefront_wide_c4terrain.json"}
+# the round-1a megakernel capture predates the JSON summaries (profiles/r1a_ncu_full_k_render_mega_c4terrain.txt)
+NCU_LEGACY = {("c4-terrain", "mega"): {"traffic": 98.76e6 + 58.22e6,
+                                       "bound_by": {"k_render_mega": {"issue_active": 0.50, "threads_per_inst": 17.96},
+                                                    "source": "profiles/r1a_ncu_full_k_render_mega_c4terrain.txt"}}}
+
+
+def ncu_figures(workload_name, kernel_set):
+    """(dram bytes per frame, {kernel: issue / L1 / divergence figures}) from the committed capture, or (None, None)."""
+    key = (workload_name, kernel_set)
+    if key in NCU_LEGACY:
+        return NCU_LEGACY[key]["traffic"], NCU_LEGACY[key]["bound_by"]
+    path = NCU_SUMMARIES.get(key)
+    if not path:
+        return None, None
+    try:
+        js = json.load(open(os.path.join(ROOT, path)))
+    except Exception:
+        return None, None
+    traffic, by = 0.0, {"source": js.get("source", path)}
+    for k in js["kernels"]:
+        traffic += k["dram_bytes"] or 0.0
+        short = k["name"].replace("void ", "").split("<")[0].split("(")[0]
+        if short == "k_wf_count":
+            continue
+        by[short] = {"issue_active": round(k["issue_active"] / 100.0, 3), "threads_per_inst": k["threads_per_inst"],
+                     "l1_lsu_wavefronts": round(k["l1_lsu_wavefronts_pct"] / 100.0, 3),
+                     "l1_hit": round(k["l1_hit"] / 100.0, 3), "l2_hit": round(k["l2_hit"] / 100.0, 3),
+                     "ms_under_ncu": k["ms"]}
+    return traffic, by
+
+
 BYTES_PER_RAY = _load_bytes_per_ray()
-# dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed `ncu --set full` captures
-# (profiles/*_ncu_full_*.txt); None where no capture exists.
-TRAFFIC_BYTES = {("c4-terrain", "mega"): 98.76e6 + 58.22e6,            # profiles/r1a_ncu_full_k_render_mega_c4terrain.txt
-                 ("c4-terrain", "wavefront"): (107.40 + 277.34 + 274.14 + 42.48) * 1e6}   # profiles/r1h_ncu_full_wavefront_c4terrain.txt   # committed output of tools/count_bytes_per_ray.py
 
 
 def workload(name):
@@ -313,7 +338,7 @@ def run_ours(args):
         achieved = rays_local * bpr / (k_ms * 1e-3) / 1e9
         wf = launches_per_step > 1
         ph = [float(x) for x in np.mean(np.asarray(phase_ms), axis=0)]
-        traffic = TRAFFIC_BYTES.get((args.workload, "wavefront" if wf else "mega"))
+        traffic, bound_by = ncu_figures(args.workload, "wavefront" if wf else "mega")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
                     "kernel": ("k_wf_primary (primary trace + shading, dominant) + k_wf_shadow; one frame = one launch "
@@ -321,14 +346,15 @@ def run_ours(args):
                     "kernel_ms": k_ms,
                     "phase_ms": {"primary_trace_and_shade": ph[0], "shadow_trace": ph[2]} if wf else None,
                     "bytes_per_ray": bpr, "rays_per_launch": rays_local, "peak_source": peak_src,
-                    # what actually bounds the kernels (from the committed ncu captures, profiles/):
+                    # what actually bounds the kernels (from the committed ncu capture):
                     "dram_frac_actual": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                    "issue_slot_utilisation": ISSUE_UTIL.get((args.workload, "wavefront" if wf else "mega")),
-                    "note": "`achieved` counts ALGORITHMIC bytes under the reference's traversal (SURVEY.md 8d), every "
-                            "box / primitive fetch of every ray; the scene is cache-resident (L1 hit 66-82 %, L2 hit "
-                            "55-66 %), so `frac` can exceed 1 and is not an HBM-efficiency claim: real DRAM traffic is "
-                            "`traffic` (dram_frac_actual of peak).  The kernels are instruction-issue bound "
-                            "(issue_slot_utilisation), see DESIGN.md section 4"}
+                    "bound_by": bound_by,
+                    "note": "`achieved` counts ALGORITHMIC bytes under the reference's traversal (SURVEY.md 8d): every "
+                            "box / primitive fetch of every ray at 32 B per box.  The scene is cache-resident, so `frac` "
+                            "can exceed 1 and is not an HBM-efficiency claim: real DRAM traffic is `traffic` "
+                            "(dram_frac_actual of peak).  The kernels are co-limited by instruction issue and by the "
+                            "L1 data pipe (one 128 B wavefront per cycle per SM; a 4-wide node is 112 B per ray per "
+                            "step): see bound_by and DESIGN.md section 4"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
