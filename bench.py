@@ -91,6 +91,14 @@ def workload(name):
     elif name == "c2":
         sc, cam = scenes.c2_bunny_proxy()
         desc = "C2: bunny proxy (69 566 triangles) + floor, 1920x1080, 1 point light, BVH 24 Midpoint, depth 1"
+    elif name == "c2-area":
+        sc, cam = scenes.c2_bunny_proxy(area_samples=1)
+        desc = ("C2 as named in BASELINE.json: bunny proxy + floor, 1920x1080, point light + quad area light (extension, 1 light "
+                "sample per pixel sample; run with --spp 16), BVH 24 Midpoint, depth 1")
+    elif name == "c5-area":
+        sc, cam = scenes.c5_replicated_bunny(area_samples=1)
+        desc = ("C5 as named in BASELINE.json: 144 copies of the bunny proxy (10M triangles), 3840x2160, point light + quad area "
+                "light (extension; run with --spp 64), BVH 40 Midpoint, depth 1")
     elif name == "c1":
         sc, cam = scenes.c1_scene_yahrr()
         desc = "C1: corrected scene.yahrr (7 spheres + floor), 512x512, 1 spp, BVH 16 Midpoint, depth 1"

@@ -89,7 +89,7 @@ renderGpu scene = do
                             | S.BlinnPhongMaterial _ _ (Vec3 dr dg db) (Vec3 sr' sg sb) sh <- mats ])) $ \mp ->
    f32 (VS.fromList (concat [ [px, py, pz, r, g, b]
                             | L.PointLight (Vec3 px py pz) (Vec3 r g b) <- S.lights scene ])) $ \lp ->
-   allocaBytes 144 $ \desc -> allocaBytes 48 $ \cptr -> alloca $ \hptr -> do
+   allocaBytes 160 $ \desc -> allocaBytes 48 $ \cptr -> alloca $ \hptr -> do
      -- struct yahr_scene_desc (offsets: see include/yahr_b200.h)
      pokeByteOff desc 0 (fromIntegral (length tris) :: Word32)
      mapM_ (\(o, p) -> pokeByteOff desc o p) (zip [8, 16 ..] [p0, p1, p2, n0, n1, n2])
@@ -101,6 +101,7 @@ renderGpu scene = do
      pokeByteOff desc 120 (fromIntegral (length (S.lights scene)) :: Word32); pokeByteOff desc 128 lp
      pokeByteOff desc 136 (fromIntegral maxDepth :: CInt)
      pokeByteOff desc 140 splitMode
+     pokeByteOff desc 144 (0 :: Word32); pokeByteOff desc 152 nullPtr   -- n_area_lights / area_lights: extension, unused by yahr
      do
        -- struct yahr_camera: imW imH focalLength lookDir[3] upDir[3] position[3]
        let Vec3 lx ly lz = C.lookDir cam; Vec3 ux uy uz = C.upDir cam; Vec3 qx qy qz = C.position cam

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define YAHR_B200_ABI_VERSION 1
+#define YAHR_B200_ABI_VERSION 2
 
 typedef enum yahr_status {
   YAHR_OK = 0,
@@ -83,6 +83,14 @@ typedef struct yahr_scene_desc {
   const float* lights;           /* n_lights x 6: position xyz, spectrum rgb (Lights.PointLight, Lights.hs:7) */
   int32_t bvh_max_depth;         /* BVH <maxDepth> _   (Culling.hs:19) */
   int32_t split_mode;            /* YAHR_SPLIT_*       (Culling.hs:18) */
+  /* EXTENSION -- no reference counterpart (the reference has point lights only, Lights.hs:7): one-sided
+   * parallelogram lights.  n_area_lights x 13 floats: corner xyz, edge1 xyz, edge2 xyz, radiance rgb,
+   * samples (>= 1, as a float).  Every sample is a virtual point light of spectrum
+   * cos_l * (area / samples) * radiance at a counter-based pseudo-random point of the parallelogram, fed
+   * through the reference's own direct-lighting arithmetic (csrc/render_device.cuh lightSampleU).
+   * 0 / NULL = none. */
+  uint32_t n_area_lights;
+  const float* area_lights;
 } yahr_scene_desc;
 
 /* Cameras.Camera (Cameras.hs:54-56).  Image size is floor(imW) x floor(imH) (main.hs:122-123). */

@@ -35,6 +35,8 @@ typedef struct {
   const float* lights;         // L x {position3, spectrum3}
   int32_t bvh_max_depth;
   int32_t split_mode;          // 0 Midpoint, 1 SurfaceAreaHeuristic
+  uint32_t n_area_lights;      // extension (no reference counterpart)
+  const float* area_lights;    // A x {corner3, edge1 3, edge2 3, radiance3, samples}
 } yo_scene_desc;
 
 typedef struct {
@@ -79,6 +81,8 @@ void* yo_scene_create(const yo_scene_desc* d) {
   }
   for (uint32_t i = 0; i < d->n_lights; ++i)
     sc->lights.push_back(Light{v3(d->lights + 6 * i), v3(d->lights + 6 * i + 3)});
+  if (d->n_area_lights && d->area_lights)
+    sc->areaLightData.assign(d->area_lights, d->area_lights + 13 * (size_t)d->n_area_lights);
   // buildCollisionModel (main.hs:41-53) + cull (main.hs:118)
   sc->bounds.resize(n);
   for (uint32_t i = 0; i < n; ++i) {
@@ -166,7 +170,9 @@ int yo_render(void* h, const yo_camera* cam, int recursion_depth, int spp, uint6
             Ray ray = computeInitialRay(caster, fu, fv);
             st.n_primary++;
             int32_t prim; float th;
-            L = vcast(*sc, recursion_depth, ray, &st, &prim, &th);
+            ShadeCtx ctx;
+            ctx.seed = seed; ctx.pixel = pixel; ctx.sample = (uint32_t)s; ctx.level = 0;
+            L = vcast(*sc, recursion_depth, ray, &st, &prim, &th, ctx);
             if (s == 0) { prim0 = prim; t0hit = th; }
             acc = vadd(acc, L);
           }

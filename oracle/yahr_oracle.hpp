@@ -247,6 +247,7 @@ struct Primitive {
 };
 struct Material { Vec3 diffuse, specular; float shininess; };   // Scene.hs:45-50; ambient is ignored (Shaders.hs:12-14)
 struct Light { Vec3 position, spectrum; };                       // Lights.hs:7
+struct AreaLight;                                                // extension, defined with the lights code below
 
 // ---------------------------------------------------------------------------------------
 // Culling.hs -- the closure tree reified as an explicit node tree.
@@ -271,6 +272,7 @@ struct Scene {
   std::vector<Primitive> prims;
   std::vector<Material> materials;
   std::vector<Light> lights;
+  std::vector<float> areaLightData;  // extension: 13 floats per area light (corner, edge1, edge2, radiance, samples)
   std::vector<BoundingBox> bounds;   // boundSceneObject, main.hs:51-53
   Bvh bvh;
 };
@@ -478,6 +480,58 @@ inline Vec3 bsdfAt(const Material& m, const DifferentialGeometry& dg, Vec3 iw, V
 }
 
 // ---------------------------------------------------------------------------------------
+// EXTENSION (no reference counterpart, "parity unpinned"): spp > 1.  The reference shoots one
+// ray through the integer raster coordinate (main.hs:73); sample 0 keeps offset (0,0) so that
+// spp = 1 is exactly the reference.  Samples s >= 1 get a counter-based PCG-hash jitter in
+// [0,1)^2.  The product kernel implements the same function.
+// ---------------------------------------------------------------------------------------
+inline uint32_t pcgHash(uint32_t x) {
+  uint32_t state = x * 747796405u + 2891336453u;
+  uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+inline float sampleOffset(uint64_t seed, uint32_t pixel, uint32_t s, uint32_t dim) {
+  if (s == 0) return 0.0f;
+  uint32_t h = pcgHash((uint32_t)(seed >> 32) ^ 0x9E3779B9u);
+  h = pcgHash(h ^ (uint32_t)seed);
+  h = pcgHash(h ^ pixel);
+  h = pcgHash(h ^ (s * 2u + dim));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------------------------------
+// EXTENSION (no reference counterpart, "parity unpinned"): quad area lights.  The reference has
+// point lights only (Lights.hs:7).  An area light is a one-sided parallelogram corner + a*edge1 +
+// b*edge2 emitting `radiance` towards edge1 x edge2; per shading point it is sampled `samples`
+// times with a counter-based PCG-hash (keyed by seed, pixel, pixel sample, recursion level, light
+// slot), and each sample point acts as a point light of spectrum  cos_l * (area / samples) * radiance
+// through the reference's own illuminationAtPoint / directIllumination arithmetic.  Light "slots"
+// are numbered point lights first, then every sample of every area light.  The product kernels
+// implement the same functions.
+// ---------------------------------------------------------------------------------------
+struct AreaLight {
+  Vec3 corner, edge1, edge2, radiance;
+  uint32_t samples;
+  Vec3 normal;     // norm (edge1 x edge2)
+  Vec3 flux;       // (area / samples) @* radiance
+};
+inline void finishAreaLight(AreaLight& a) {
+  Vec3 n = cross(a.edge1, a.edge2);
+  float area = len(n);
+  a.normal = scale(1.0f / area, n);
+  a.flux = scale(area / (float)a.samples, a.radiance);
+}
+struct ShadeCtx { uint64_t seed = 0; uint32_t pixel = 0, sample = 0, level = 0; };
+inline float lightSampleU(const ShadeCtx& c, uint32_t slot, uint32_t dim) {
+  uint32_t h = pcgHash((uint32_t)(c.seed >> 32) ^ 0x9E3779B9u);
+  h = pcgHash(h ^ (uint32_t)c.seed);
+  h = pcgHash(h ^ c.pixel);
+  h = pcgHash(h ^ (0x80000000u | (c.sample * 2u + 1u)));
+  h = pcgHash(h ^ ((c.level << 24) ^ (slot * 2u + dim)));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------------------------------
 // Lights.hs:15-24, Integrators.hs
 // ---------------------------------------------------------------------------------------
 struct LightSample { Vec3 dir, intensity; Vec3 shadowOrigin, lightPos; };
@@ -486,10 +540,25 @@ inline Vec3 reflectionDir(Vec3 u, Vec3 n) {                 // Integrators.hs:46
   return vsub(u, scale(2.0f * dot(u, n), n));               // u - 2 * (u .* n) @* n
 }
 
+inline std::vector<AreaLight> areaLightsOf(const Scene& sc) {
+  std::vector<AreaLight> out;
+  for (size_t i = 0; i + 13 <= sc.areaLightData.size(); i += 13) {
+    const float* f = sc.areaLightData.data() + i;
+    AreaLight a;
+    a.corner = Vec3{f[0], f[1], f[2]}; a.edge1 = Vec3{f[3], f[4], f[5]}; a.edge2 = Vec3{f[6], f[7], f[8]};
+    a.radiance = Vec3{f[9], f[10], f[11]};
+    a.samples = (uint32_t)f[12];
+    finishAreaLight(a);
+    out.push_back(a);
+  }
+  return out;
+}
+
 inline Vec3 directIllumination(const Scene& sc, const DifferentialGeometry& dg, const Ray& ray,
-                               const Material& bsdf, Stats* st) {       // Integrators.hs:50-61
+                               const Material& bsdf, Stats* st, const ShadeCtx& ctx = ShadeCtx()) {  // Integrators.hs:50-61
   Vec3 x = dg.dgPoint, n = dg.dgNormal;
   Vec3 total = vof(0.0f);                                   // sum = foldl (+) 0
+  uint32_t slot = 0;
   for (const Light& light : sc.lights) {
     if (st) st->n_light++;
     // illuminationAtPoint (Lights.hs:15-24)
@@ -504,13 +573,38 @@ inline Vec3 directIllumination(const Scene& sc, const DifferentialGeometry& dg, 
       if (unoccluded) contrib = vmul(scale(std::fabs(dot(lightDir, n)), k), intensity);
     }
     total = vadd(total, contrib);
+    ++slot;
+  }
+  // extension: area lights, one virtual point light per sample
+  if (!sc.areaLightData.empty()) {
+    for (const AreaLight& al : areaLightsOf(sc)) {
+      for (uint32_t j = 0; j < al.samples; ++j, ++slot) {
+        if (st) st->n_light++;
+        float u1 = lightSampleU(ctx, slot, 0), u2 = lightSampleU(ctx, slot, 1);
+        Vec3 lightPos = vadd(vadd(al.corner, scale(u1, al.edge1)), scale(u2, al.edge2));
+        Vec3 pointToLight = vsub(lightPos, x);
+        Vec3 lightDir = norm(pointToLight);
+        float cosL = -dot(lightDir, al.normal);
+        Vec3 k = bsdfAt(bsdf, dg, lightDir, vneg(ray.u));
+        Vec3 contrib = vof(0.0f);
+        if (lensq(k) > 0 && cosL > 0) {
+          if (st) st->n_shadow++;
+          bool unoccluded = reachable(sc, vadd(x, scale(0.001f, lightDir)), lightPos, st);
+          if (unoccluded) {
+            Vec3 intensity = scale(1.0f / lensq(pointToLight), scale(cosL, al.flux));
+            contrib = vmul(scale(std::fabs(dot(lightDir, n)), k), intensity);
+          }
+        }
+        total = vadd(total, contrib);
+      }
+    }
   }
   return total;
 }
 
 // radiance / vcast / vhit (Integrators.hs:22-43).  `primOut`/`tOut` receive the primary hit.
 inline Vec3 vcast(const Scene& sc, int maxDepth, const Ray& ray, Stats* st, int32_t* primOut = nullptr,
-                  float* tOut = nullptr) {
+                  float* tOut = nullptr, ShadeCtx ctx = ShadeCtx()) {
   if (primOut) *primOut = -1;
   if (tOut) *tOut = 0.0f;
   if (maxDepth == 0) return vof(0.0f);                      // vcast 0 _ = Vec3 0 0 0
@@ -527,10 +621,12 @@ inline Vec3 vcast(const Scene& sc, int maxDepth, const Ray& ray, Stats* st, int3
   Vec3 fr = bsdfAt(bsdf, dg, r, vneg(ray.u));               // f r
   Ray next{vadd(x, scale(0.001f, r)), r, 1e6f};
   if (st && maxDepth - 1 > 0) st->n_secondary++;
-  Vec3 rs = vcast(sc, maxDepth - 1, next, st);              // strict: always evaluated
+  ShadeCtx deeper = ctx;
+  deeper.level = ctx.level + 1;
+  Vec3 rs = vcast(sc, maxDepth - 1, next, st, nullptr, nullptr, deeper);   // strict: always evaluated
   // (n .* r) @* f r * rs + directIllumination ...   ==  (((n.r) @* f r) * rs) + direct
   Vec3 refl = vmul(scale(dot(n, r), fr), rs);
-  return vadd(refl, directIllumination(sc, dg, ray, bsdf, st));
+  return vadd(refl, directIllumination(sc, dg, ray, bsdf, st, ctx));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -629,26 +725,6 @@ inline int64_t numBatches(int64_t numThreads, int64_t width, int64_t height) {
   int64_t m = (32 * numThreads > width) ? 32 * numThreads : width;
   if ((m * height) / 256 < 1) return 1;   // the reference dies here (2 ^ negative); one tile instead
   return roundUpPow2((m * height) / 256);
-}
-
-// ---------------------------------------------------------------------------------------
-// EXTENSION (no reference counterpart, "parity unpinned"): spp > 1.  The reference shoots one
-// ray through the integer raster coordinate (main.hs:73); sample 0 keeps offset (0,0) so that
-// spp = 1 is exactly the reference.  Samples s >= 1 get a counter-based PCG-hash jitter in
-// [0,1)^2.  The product kernel implements the same function.
-// ---------------------------------------------------------------------------------------
-inline uint32_t pcgHash(uint32_t x) {
-  uint32_t state = x * 747796405u + 2891336453u;
-  uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
-  return (word >> 22u) ^ word;
-}
-inline float sampleOffset(uint64_t seed, uint32_t pixel, uint32_t s, uint32_t dim) {
-  if (s == 0) return 0.0f;
-  uint32_t h = pcgHash((uint32_t)(seed >> 32) ^ 0x9E3779B9u);
-  h = pcgHash(h ^ (uint32_t)seed);
-  h = pcgHash(h ^ pixel);
-  h = pcgHash(h ^ (s * 2u + dim));
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
 }  // namespace yo

@@ -83,7 +83,18 @@ SMALL = {
     "adversarial": lambda: scenes.adversarial_shared_edges(),
     "adversarial-sah": lambda: scenes.adversarial_shared_edges(split_mode=1),
     "adversarial-depth3": lambda: _with(scenes.adversarial_shared_edges(128, 128), bvh_max_depth=3),
+    # extension (no reference counterpart): quad area lights, alone and next to point lights
+    "bunny-area": lambda: scenes.c2_bunny_proxy(256, 144, nu=40, nv=20, area_samples=4),
+    "c1-area-only": lambda: _area_only(scenes.c1_scene_yahrr(192, 192)),
 }
+
+
+def _area_only(sc_cam):
+    sc, cam = sc_cam
+    sc = dict(sc)
+    sc["lights"] = np.zeros((0, 6), np.float32)
+    scenes.add_area_light(sc, [2, 9, -12], [4, 0, 0], [0, 0, 4], [30, 30, 30], 1)
+    return sc, cam
 
 
 def _with(sc_cam, **kw):
@@ -193,6 +204,9 @@ def test_wide_tree_is_a_collapse_of_the_reference_tree(name):
 def test_parity_recursion_depth(depth):
     """Whitted recursion (Integrators.hs:37-43); scene.yahrr ships with depth 3."""
     sc, cam = scenes.c1_scene_yahrr(256, 192)
+    if depth == 2:        # also with an area light (extension): the sample points depend on the recursion level
+        sc = dict(sc)
+        scenes.add_area_light(sc, [2, 9, -12], [4, 0, 0], [0, 0, 4], [30, 30, 30], 3)
     o = ob.OracleScene(sc)
     orgb, opid, _, ost = o.render(cam, recursion_depth=depth)
     o.close()
@@ -205,7 +219,7 @@ def test_parity_recursion_depth(depth):
 
 def test_parity_spp_extension():
     """spp > 1 (extension): same counter-based jitter in oracle and kernel; sample 0 = reference ray."""
-    sc, cam = scenes.c2_bunny_proxy(160, 90, nu=40, nv=20)
+    sc, cam = scenes.c2_bunny_proxy(160, 90, nu=40, nv=20, area_samples=2)
     o = ob.OracleScene(sc)
     orgb, opid, _, _ = o.render(cam, spp=4, seed=0x1234ABCD5678)
     o1rgb, o1pid, _, _ = o.render(cam, spp=1)

@@ -128,7 +128,7 @@ def test_abi_exports_every_declared_symbol():
     L = C.CDLL(api.LIB_PATH)
     for n in sorted(names):
         assert hasattr(L, n), "missing export " + n
-    assert api.lib().yahr_b200_abi_version() == 1
+    assert api.lib().yahr_b200_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -39,6 +39,7 @@ class SceneDesc(C.Structure):
         ("n_materials", C.c_uint32), ("materials", _f32p),
         ("n_lights", C.c_uint32), ("lights", _f32p),
         ("bvh_max_depth", C.c_int32), ("split_mode", C.c_int32),
+        ("n_area_lights", C.c_uint32), ("area_lights", _f32p),
     ]
 
 
@@ -192,6 +193,7 @@ def scene_desc(scene):
     d.lights, d.n_lights = fp("lights", 6)
     d.bvh_max_depth = int(_get(scene, "bvh_max_depth", 16))
     d.split_mode = int(_get(scene, "split_mode", 0))
+    d.area_lights, d.n_area_lights = fp("area_lights", 13)      # extension: quad area lights
     return d, keep
 
 

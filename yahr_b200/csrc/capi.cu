@@ -84,6 +84,7 @@ struct yahr_scene {
   uint2* d_multi = nullptr;
   float4* d_materials = nullptr;
   float4* d_lights = nullptr;
+  float4* d_areaLights = nullptr;
   unsigned long long* d_counters = nullptr;
   uint32_t* d_order = nullptr;            // primitive ID per DFS position (inspection)
   yahr_scene_info info{};
@@ -110,7 +111,7 @@ struct yahr_scene {
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
-    cudaFree(d_lights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
+    cudaFree(d_lights); cudaFree(d_areaLights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); cudaFree(kv.second.d_itemPixels); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
@@ -220,7 +221,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
 
   if (plan.wavefront) {
     WavefrontParams& W = plan.W;
-    const uint32_t nL = sc->dev.nLights;
+    const uint32_t nL = sc->dev.nSlots;          // light slots: point lights + every area-light sample
     plan.entriesPerItem = nL > 1 ? nL : 1;
     const size_t px = (size_t)cs.width * cs.height;
     if (opts->spp > 1 && px > sc->wfPixels) {
@@ -340,6 +341,41 @@ void attachWideTree(yahr_scene* sc) {
   sc->info.build_ms += nowMs() - t0;
 }
 
+// Extension: quad area lights (include/yahr_b200.h).  normal = norm (edge1 x edge2) and flux = (area / samples) @*
+// radiance are computed here once, in binary32, cross -> sqrt (dot n n) -> scale, in that order.
+int uploadAreaLights(yahr_scene* sc, const yahr_scene_desc* desc, uint64_t& bytes) {
+  sc->dev.areaLights = nullptr; sc->dev.nAreaLights = 0; sc->dev.nSlots = desc->n_lights;
+  if (desc->n_area_lights == 0) return YAHR_OK;
+  if (!desc->area_lights) return fail(YAHR_ERR_INVALID_ARGUMENT, "area_lights missing");
+  std::vector<float4> recs(5 * (size_t)desc->n_area_lights);
+  uint64_t slots = desc->n_lights;
+  for (uint32_t a = 0; a < desc->n_area_lights; ++a) {
+    const float* f = desc->area_lights + 13 * (size_t)a;
+    for (int k = 0; k < 13; ++k)
+      if (!std::isfinite(f[k])) return fail(YAHR_ERR_NON_FINITE_INPUT, "non-finite area light");
+    if (!(f[12] >= 1.0f && f[12] <= 4096.0f)) return fail(YAHR_ERR_INVALID_ARGUMENT, "area light samples must be in [1, 4096]");
+    const uint32_t samples = (uint32_t)f[12];
+    const f3 corner{f[0], f[1], f[2]}, e1{f[3], f[4], f[5]}, e2{f[6], f[7], f[8]}, radiance{f[9], f[10], f[11]};
+    const f3 n = cross(e1, e2);
+    const float area = std::sqrt(dot(n, n));
+    if (!(area > 0.0f)) return fail(YAHR_ERR_INVALID_ARGUMENT, "degenerate area light");
+    const f3 normal = (1.0f / area) * n;
+    const f3 flux = (area / (float)samples) * radiance;
+    float sbits;
+    std::memcpy(&sbits, &samples, 4);
+    recs[5 * a + 0] = make_float4(corner.x, corner.y, corner.z, sbits);
+    recs[5 * a + 1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+    recs[5 * a + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    recs[5 * a + 3] = make_float4(normal.x, normal.y, normal.z, 0.0f);
+    recs[5 * a + 4] = make_float4(flux.x, flux.y, flux.z, 0.0f);
+    slots += samples;
+  }
+  if (slots > 65535) return fail(YAHR_ERR_INVALID_ARGUMENT, "more than 65535 light slots");
+  sc->d_areaLights = devUpload(recs, bytes);
+  sc->dev.areaLights = sc->d_areaLights; sc->dev.nAreaLights = desc->n_area_lights; sc->dev.nSlots = (uint32_t)slots;
+  return YAHR_OK;
+}
+
 // Small per-scene tables (materials, lights), events, counters: shared by both build paths.
 void uploadSmallTables(yahr_scene* sc, const yahr_scene_desc* desc, uint64_t& bytes) {
   std::vector<float4> mats(2 * (size_t)desc->n_materials), lights(2 * (size_t)desc->n_lights);
@@ -432,6 +468,7 @@ int createSceneOnDevice(const yahr_scene_desc* d, yahr_scene** out) {
     bo.flat = nullptr; bo.prims = nullptr; bo.normals = nullptr; bo.multi = nullptr; bo.order = nullptr;
     uint64_t bytes = (uint64_t)bo.nInner * 64 + (uint64_t)n * 96 + (uint64_t)bo.nMulti * 8 + (uint64_t)n * 4;
     uploadSmallTables(sc, d, bytes);
+    { int rcA = uploadAreaLights(sc, d, bytes); if (rcA) { delete sc; return rcA; } }
     sc->dev.nodes = sc->d_nodes; sc->dev.prims = sc->d_prims; sc->dev.normals = sc->d_normals;
     sc->dev.multiLeaves = sc->d_multi;
     sc->dev.rootRef = n ? bo.rootRef : kDevRefNull;
@@ -560,6 +597,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     sc->dev.nodes = sc->d_nodes; sc->dev.prims = sc->d_prims; sc->dev.normals = sc->d_normals;
     sc->dev.multiLeaves = sc->d_multi; sc->dev.materials = sc->d_materials; sc->dev.lights = sc->d_lights;
     sc->dev.nLights = desc->n_lights;
+    { int rcA = uploadAreaLights(sc, desc, bytes); if (rcA) { delete sc; return rcA; } }
     sc->dev.rootRef = bvh.rootRef;
     sc->dev.rootLo[0] = bvh.rootBox.lo.x; sc->dev.rootLo[1] = bvh.rootBox.lo.y; sc->dev.rootLo[2] = bvh.rootBox.lo.z;
     sc->dev.rootHi[0] = bvh.rootBox.hi.x; sc->dev.rootHi[1] = bvh.rootBox.hi.y; sc->dev.rootHi[2] = bvh.rootBox.hi.z;

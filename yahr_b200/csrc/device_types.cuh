@@ -26,6 +26,9 @@ namespace yb {
 //   multiLeaves : (first, count) per multi-leaf
 //   materials : 2 x float4 = (diffuse.rgb, shininess), (specular.rgb, 0)
 //   lights    : 2 x float4 = (position.xyz, 0), (spectrum.rgb, 0)
+//   areaLights: 5 x float4 = (corner.xyz, samples as bits), (edge1.xyz, 0), (edge2.xyz, 0),
+//               (normal.xyz, 0), (flux.rgb, 0)      -- extension, see include/yahr_b200.h
+//   Light SLOTS number the point lights first, then every sample of every area light (nSlots in all).
 struct DeviceScene {
   const float4* nodes;
   const float4* wide;
@@ -34,7 +37,10 @@ struct DeviceScene {
   const uint2* multiLeaves;
   const float4* materials;
   const float4* lights;
+  const float4* areaLights;
   uint32_t nLights;
+  uint32_t nAreaLights;
+  uint32_t nSlots;
   uint32_t rootRef;
   float rootLo[3], rootHi[3];
 };

@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ Ren
       const Ray ray = cameraRay(P, fu, fv);
       cnt.primary++;
       uint32_t prim;
-      L = radiance<ORDERED>(P, ray, cnt, prim);
+      ShadeCtx ctx;
+      ctx.seed = P.seed; ctx.pixel = pixel; ctx.sample = (uint32_t)s; ctx.level = 0;
+      L = radiance<ORDERED>(P, ray, cnt, prim, ctx);
       if (s == 0) prim0 = prim;
       acc = vadd(acc, L);
     }

@@ -277,34 +277,91 @@ __device__ __forceinline__ V3 bsdfAt(const MaterialD& m, const Frame& f, V3 iw, 
   return vadd(vadd(mk(0.0f, 0.0f, 0.0f), a), b);
 }
 
+// Counter-based jitter for samples >= 1 (extension; sample 0 = the reference's ray).
+__device__ __forceinline__ uint32_t pcgHash(uint32_t x) {
+  const uint32_t state = x * 747796405u + 2891336453u;
+  const uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float sampleOffset(uint64_t seed, uint32_t pixel, uint32_t s, uint32_t dim) {
+  if (s == 0) return 0.0f;
+  uint32_t h = pcgHash((uint32_t)(seed >> 32) ^ 0x9E3779B9u);
+  h = pcgHash(h ^ (uint32_t)seed);
+  h = pcgHash(h ^ pixel);
+  h = pcgHash(h ^ (s * 2u + dim));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// Extension: quad area lights (include/yahr_b200.h).  The coordinates
+// of the sample point of light slot `slot` on its parallelogram, keyed by pixel / pixel sample / level.
+struct ShadeCtx { uint64_t seed; uint32_t pixel, sample, level; };
+__device__ __forceinline__ float lightSampleU(const ShadeCtx& c, uint32_t slot, uint32_t dim) {
+  uint32_t h = pcgHash((uint32_t)(c.seed >> 32) ^ 0x9E3779B9u);
+  h = pcgHash(h ^ (uint32_t)c.seed);
+  h = pcgHash(h ^ c.pixel);
+  h = pcgHash(h ^ (0x80000000u | (c.sample * 2u + 1u)));
+  h = pcgHash(h ^ ((c.level << 24) ^ (slot * 2u + dim)));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+struct AreaLightD { V3 corner, edge1, edge2, normal, flux; uint32_t samples; };
+__device__ __forceinline__ AreaLightD loadAreaLight(const DeviceScene& sc, uint32_t a) {
+  const float4 r0 = __ldg(&sc.areaLights[5 * a + 0]);
+  AreaLightD l;
+  l.corner = xyz(r0); l.samples = __float_as_uint(r0.w);
+  l.edge1 = xyz(__ldg(&sc.areaLights[5 * a + 1])); l.edge2 = xyz(__ldg(&sc.areaLights[5 * a + 2]));
+  l.normal = xyz(__ldg(&sc.areaLights[5 * a + 3])); l.flux = xyz(__ldg(&sc.areaLights[5 * a + 4]));
+  return l;
+}
+__device__ __forceinline__ V3 areaLightPoint(const AreaLightD& l, const ShadeCtx& ctx, uint32_t slot) {
+  const float u1 = lightSampleU(ctx, slot, 0), u2 = lightSampleU(ctx, slot, 1);
+  return vadd(vadd(l.corner, vscale(u1, l.edge1)), vscale(u2, l.edge2));
+}
+
 struct Counters { uint32_t primary, shadow, secondary; };
 
 // directIllumination (Integrators.hs:50-61) + illuminationAtPoint (Lights.hs:15-24) + reachable (Rays.hs:49-54)
+// for one light slot: a point light (spectrum = its spectrum) or one sample of an area light (extension:
+// spectrum = its flux, scaled by the emitter cosine; nothing is emitted from the back side).
+template <bool ORDERED>
+__device__ __forceinline__ V3 slotIllumination(const DeviceScene& sc, const Surface& s, const Frame& f,
+                                               const MaterialD& m, V3 wo, V3 lightPos, V3 spectrum, bool area,
+                                               V3 lightNormal, Counters& cnt) {
+  const V3 pointToLight = vsub(lightPos, s.x);
+  const V3 lightDir = vnorm(pointToLight);
+  const V3 k = bsdfAt(m, f, lightDir, wo);
+  const float cosL = area ? -dot(lightDir, lightNormal) : 1.0f;
+  V3 contrib = mk(0.0f, 0.0f, 0.0f);
+  if (lensq(k) > 0.0f && (!area || cosL > 0.0f)) {
+    const V3 p0 = vadd(s.x, vscale(0.001f, lightDir));
+    const V3 dl = vsub(lightPos, p0);
+    const Ray probe = makeRay(p0, vnorm(dl));
+    float th;
+    cnt.shadow++;
+    const bool occluded = traverse<true, ORDERED>(sc, probe, len(dl), th) != kNoHit;
+    if (!occluded) {
+      const V3 intensity = vscale(rcp(lensq(pointToLight)), area ? vscale(cosL, spectrum) : spectrum);
+      contrib = vmul(vscale(fabsf(dot(lightDir, s.n)), k), intensity);
+    }
+  }
+  return contrib;
+}
+
 template <bool ORDERED>
 __device__ __forceinline__ V3 directIllumination(const DeviceScene& sc, const Surface& s, const Frame& f,
-                                                 const MaterialD& m, V3 rayDir, Counters& cnt) {
+                                                 const MaterialD& m, V3 rayDir, Counters& cnt, const ShadeCtx& ctx) {
   V3 total = mk(0.0f, 0.0f, 0.0f);
   const V3 wo = vneg(rayDir);
-  for (uint32_t li = 0; li < sc.nLights; ++li) {
+  uint32_t slot = 0;
+  for (uint32_t li = 0; li < sc.nLights; ++li, ++slot) {
     const V3 lightPos = xyz(__ldg(&sc.lights[2 * li + 0]));
     const V3 spectrum = xyz(__ldg(&sc.lights[2 * li + 1]));
-    const V3 pointToLight = vsub(lightPos, s.x);
-    const V3 lightDir = vnorm(pointToLight);
-    const V3 k = bsdfAt(m, f, lightDir, wo);
-    V3 contrib = mk(0.0f, 0.0f, 0.0f);
-    if (lensq(k) > 0.0f) {
-      const V3 p0 = vadd(s.x, vscale(0.001f, lightDir));
-      const V3 dl = vsub(lightPos, p0);
-      const Ray probe = makeRay(p0, vnorm(dl));
-      float th;
-      cnt.shadow++;
-      const bool occluded = traverse<true, ORDERED>(sc, probe, len(dl), th) != kNoHit;
-      if (!occluded) {
-        const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
-        contrib = vmul(vscale(fabsf(dot(lightDir, s.n)), k), intensity);
-      }
-    }
-    total = vadd(total, contrib);
+    total = vadd(total, slotIllumination<ORDERED>(sc, s, f, m, wo, lightPos, spectrum, false, mk(0, 0, 0), cnt));
+  }
+  for (uint32_t a = 0; a < sc.nAreaLights; ++a) {
+    const AreaLightD l = loadAreaLight(sc, a);
+    for (uint32_t j = 0; j < l.samples; ++j, ++slot)
+      total = vadd(total, slotIllumination<ORDERED>(sc, s, f, m, wo, areaLightPoint(l, ctx, slot), l.flux, true,
+                                                    l.normal, cnt));
   }
   return total;
 }
@@ -325,26 +382,11 @@ __device__ __forceinline__ Ray cameraRay(const RenderParams& P, float u, float v
   return makeRay(origin, vnorm(direction));
 }
 
-// Counter-based jitter for samples >= 1 (extension; sample 0 = the reference's ray).
-__device__ __forceinline__ uint32_t pcgHash(uint32_t x) {
-  const uint32_t state = x * 747796405u + 2891336453u;
-  const uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
-  return (word >> 22u) ^ word;
-}
-__device__ __forceinline__ float sampleOffset(uint64_t seed, uint32_t pixel, uint32_t s, uint32_t dim) {
-  if (s == 0) return 0.0f;
-  uint32_t h = pcgHash((uint32_t)(seed >> 32) ^ 0x9E3779B9u);
-  h = pcgHash(h ^ (uint32_t)seed);
-  h = pcgHash(h ^ pixel);
-  h = pcgHash(h ^ (s * 2u + dim));
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
-
 // radiance / vcast / vhit (Integrators.hs:22-43), recursion unrolled into a forward pass that
 // records (weight, direct) per level and a backward fold  acc = weight * acc + direct, which is
 // the reference's  ((n.r) @* f r) * rs + direct  evaluated innermost first.
 template <bool ORDERED>
-__device__ __forceinline__ V3 radiance(const RenderParams& P, Ray ray, Counters& cnt, uint32_t& primOut) {
+__device__ __forceinline__ V3 radiance(const RenderParams& P, Ray ray, Counters& cnt, uint32_t& primOut, ShadeCtx ctx) {
   V3 weight[16], direct[16];
   int levels = 0;
   primOut = kNoHit;
@@ -359,7 +401,8 @@ __device__ __forceinline__ V3 radiance(const RenderParams& P, Ray ray, Counters&
     const V3 refl = vsub(ray.d, vscale(2.0f * dot(ray.d, s.n), s.n));     // reflectionDir
     const V3 fr = bsdfAt(m, f, refl, vneg(ray.d));
     weight[levels] = vscale(dot(s.n, refl), fr);
-    direct[levels] = directIllumination<ORDERED>(P.sc, s, f, m, ray.d, cnt);
+    ctx.level = (uint32_t)level;
+    direct[levels] = directIllumination<ORDERED>(P.sc, s, f, m, ray.d, cnt, ctx);
     ++levels;
     if (level + 1 < P.depth) {
       cnt.secondary++;

@@ -347,6 +347,7 @@ __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, u
 
 // Shades the hit of one lane (all 32 lanes call this together) and emits its shadow probes.
 // vhit / directIllumination (Integrators.hs:32-61) up to the point where `reachable` is needed.
+template <bool AREA>
 __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool valid, uint32_t item, uint32_t pixel,
                                              const Ray& r, float tHit, uint32_t idx, unsigned lane) {
   const DeviceScene& sc = W.base.sc;
@@ -375,29 +376,29 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       nanBits = (base.x != base.x ? 1u : 0u) | (base.y != base.y ? 2u : 0u) | (base.z != base.z ? 4u : 0u);
     }
   }
-  // one probe per light with lensq k > 0.  single light: compacted queue (warp-aggregated append);
-  // several lights: dense slots entry = item * nLights + light so that k_wf_resolve can sum in order.
+  // one probe per light SLOT with lensq k > 0 (point lights, then every sample of every area light -- the
+  // extension of include/yahr_b200.h).  A single slot: compacted queue (warp-aggregated append); several:
+  // dense entries item * nSlots + slot so that k_wf_resolve can sum them in slot order.
   uint32_t nEmit = 0;
-  for (uint32_t li = 0; li < sc.nLights; ++li) {
+  auto doSlot = [&](uint32_t slot, V3 lightPos, V3 spectrum, bool area, V3 lightNormal) {
     bool emit = false;
     V3 p0 = mk(0, 0, 0), dl = mk(0, 0, 0), contrib = mk(0, 0, 0);
     if (hit) {
-      const V3 lightPos = xyz(__ldg(&sc.lights[2 * li + 0]));
-      const V3 spectrum = xyz(__ldg(&sc.lights[2 * li + 1]));
       const V3 pointToLight = vsub(lightPos, surf.x);
       const V3 lightDir = vnorm(pointToLight);
       const V3 k = bsdfAt(mat, fr, lightDir, wo);
-      if (lensq(k) > 0.0f) {
+      const float cosL = area ? -dot(lightDir, lightNormal) : 1.0f;
+      if (lensq(k) > 0.0f && (!area || cosL > 0.0f)) {
         emit = true;
         p0 = vadd(surf.x, vscale(0.001f, lightDir));
         dl = vsub(lightPos, p0);
-        const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
+        const V3 intensity = vscale(rcp(lensq(pointToLight)), area ? vscale(cosL, spectrum) : spectrum);
         contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
       }
     }
     uint32_t e = 0;
     if (W.dense) {
-      e = item * sc.nLights + li;
+      e = item * sc.nSlots + slot;
       if (valid && !emit) W.q0[e] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);     // empty slot
     } else {
       const unsigned m = __ballot_sync(kFull, emit);
@@ -415,6 +416,17 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       W.q1[e] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
       W.q2[e] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(nanBits));
       ++nEmit;
+    }
+  };
+  uint32_t slot = 0;
+  for (uint32_t li = 0; li < sc.nLights; ++li, ++slot)
+    doSlot(slot, xyz(__ldg(&sc.lights[2 * li + 0])), xyz(__ldg(&sc.lights[2 * li + 1])), false, mk(0, 0, 0));
+  if (AREA) {
+    ShadeCtx ctx;
+    ctx.seed = W.base.seed; ctx.pixel = pixel; ctx.sample = W.sample; ctx.level = 0;
+    for (uint32_t a = 0; a < sc.nAreaLights; ++a) {
+      const AreaLightD l = loadAreaLight(sc, a);
+      for (uint32_t j = 0; j < l.samples; ++j, ++slot) doSlot(slot, areaLightPoint(l, ctx, slot), l.flux, true, l.normal);
     }
   }
   const uint32_t warpEmit = __reduce_add_sync(kFull, nEmit);    // shadow-ray count for the stats
@@ -440,7 +452,7 @@ __device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, int MIN_BLOCKS, bool WIDE>
+template <bool ORDERED, int MIN_BLOCKS, bool WIDE, bool AREA>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
@@ -465,7 +477,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     }
     if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
-    shadeAndEmit(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
+    shadeAndEmit<AREA>(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
   }
 }
 
@@ -474,7 +486,7 @@ template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t nEntries = W.dense ? W.nItems * W.base.sc.nLights : W.work[2];
+  const uint32_t nEntries = W.dense ? W.nItems * W.base.sc.nSlots : W.work[2];
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&W.work[1], 32u);
@@ -505,7 +517,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
 __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WavefrontParams W) {
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= W.nItems) return;
-  const uint32_t nL = W.base.sc.nLights;
+  const uint32_t nL = W.base.sc.nSlots;
   V3 total = mk(0.0f, 0.0f, 0.0f);
   bool any = false;
   uint32_t pixel = 0;
@@ -582,11 +594,18 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
     if (timed) cudaEventRecord(phaseEvents[0], stream);
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
-    if (wide)
-      launchPersistent(W.capRegisters ? k_wf_primary<false, 8, true> : k_wf_primary<false, 1, true>, W, numSMs, stream);
+    // AREA: the scene has area lights (extension); kept out of the default instantiation
+    const bool area = W.base.sc.nAreaLights != 0;
+    if (area)
+      launchPersistent(wide ? k_wf_primary<false, 8, true, true>
+                            : (ordered ? k_wf_primary<true, 8, false, true> : k_wf_primary<false, 8, false, true>),
+                       W, numSMs, stream);
+    else if (wide)
+      launchPersistent(W.capRegisters ? k_wf_primary<false, 8, true, false> : k_wf_primary<false, 1, true, false>, W, numSMs,
+                       stream);
     else
-      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false> : k_wf_primary<false, 8, false>)
-                                      : (ordered ? k_wf_primary<true, 1, false> : k_wf_primary<false, 1, false>),
+      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false, false> : k_wf_primary<false, 8, false, false>)
+                                      : (ordered ? k_wf_primary<true, 1, false, false> : k_wf_primary<false, 1, false, false>),
                        W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);

@@ -44,7 +44,17 @@ def _empty_scene():
     return dict(tri_p0=z3, tri_p1=z3, tri_p2=z3, tri_n0=z3, tri_n1=z3, tri_n2=z3,
                 tri_material=np.zeros(0, np.uint32), sph_center=z3, sph_radius=np.zeros(0, F),
                 sph_material=np.zeros(0, np.uint32), prim_order=None,
-                materials=np.zeros((0, 7), F), lights=np.zeros((0, 6), F), bvh_max_depth=16, split_mode=0)
+                materials=np.zeros((0, 7), F), lights=np.zeros((0, 6), F), bvh_max_depth=16, split_mode=0,
+                area_lights=np.zeros((0, 13), F))
+
+
+def add_area_light(scene, corner, edge1, edge2, radiance, samples):
+    """EXTENSION (no reference counterpart): appends a one-sided parallelogram light emitting towards
+    edge1 x edge2 (row = corner, edge1, edge2, radiance, samples; include/yahr_b200.h)."""
+    row = np.array([list(corner) + list(edge1) + list(edge2) + list(radiance) + [float(samples)]], F)
+    prev = scene.get("area_lights")
+    scene["area_lights"] = row if prev is None or len(prev) == 0 else np.concatenate([np.asarray(prev, F), row]).astype(F)
+    return scene
 
 
 def _camera(w, h, focal, look, up, pos):
@@ -174,9 +184,10 @@ def bunny_proxy_mesh(nu=187, nv=186, seed=0xB0221E, center=(0.0, 1.05, 0.0)):
     return pts, tris, vn
 
 
-def c2_bunny_proxy(width=1920, height=1080, nu=187, nv=186, bvh_depth=24):
+def c2_bunny_proxy(width=1920, height=1080, nu=187, nv=186, bvh_depth=24, area_samples=0):
     """C2: bunny proxy (69 564 triangles at the default size) on the 2-triangle floor, exporter
-    default material (render_engine.py:15-20), focalLength 2 (render_engine.py:157), one point light."""
+    default material (render_engine.py:15-20), focalLength 2 (render_engine.py:157), one point light;
+    area_samples > 0 adds the quad area light of the BASELINE config (extension) with that many samples."""
     pts, tris, vn = bunny_proxy_mesh(nu, nv)
     sc = _empty_scene()
     fp0, fp1, fp2, fn = _floor(0.0)
@@ -193,6 +204,8 @@ def c2_bunny_proxy(width=1920, height=1080, nu=187, nv=186, bvh_depth=24):
     sc["materials"] = np.array([[1, 1, 1, 0.3, 0.3, 0.3, 1],           # __default__ (exporter)
                                 [0.8, 0.8, 0.8, 0.1, 0.1, 0.1, 20]], F)  # floor
     sc["lights"] = np.array([[4, 8, -6, 140, 140, 140]], F)
+    if area_samples:      # a 2 x 2 panel above and to the left of the model, facing down
+        add_area_light(sc, [-4.0, 5.0, -2.0], [2, 0, 0], [0, 0, 2], [12, 12, 12], area_samples)
     sc["bvh_max_depth"] = bvh_depth
     cam = _camera(width, height, 2.0, [-0.14, -0.12, 1.0], [0, 1, 0], [0.8, 1.7, -5.5])
     return sc, cam
@@ -281,7 +294,7 @@ def c4_soup(n=1_000_000, width=3840, height=2160, seed=42, bvh_depth=32, half=50
 # ------------------------------------------------------------------------------------------
 # C5: replicated bunny proxy (no instancing exists in Scene.hs, so real triangles)
 # ------------------------------------------------------------------------------------------
-def c5_replicated_bunny(copies=12, width=3840, height=2160, nu=187, nv=186, bvh_depth=40, spacing=3.0):
+def c5_replicated_bunny(copies=12, width=3840, height=2160, nu=187, nv=186, bvh_depth=40, spacing=3.0, area_samples=0):
     pts, tris, vn = bunny_proxy_mesh(nu, nv, center=(0.0, 1.05, 0.0))
     p = [pts[tris[:, k]] for k in range(3)]
     nn = [vn[tris[:, k]] for k in range(3)]
@@ -306,6 +319,9 @@ def c5_replicated_bunny(copies=12, width=3840, height=2160, nu=187, nv=186, bvh_
     sc["materials"] = np.array([[1, 1, 1, 0.3, 0.3, 0.3, 1], [0.8, 0.8, 0.8, 0.1, 0.1, 0.1, 20]], F)
     span = copies * spacing
     sc["lights"] = np.array([[0.3 * span, 1.2 * span, -0.2 * span, 3 * span * span, 3 * span * span, 3 * span * span]], F)
+    if area_samples:      # one large panel over the field, facing down (extension)
+        add_area_light(sc, [-0.25 * span, 0.9 * span, 0.25 * span], [0.5 * span, 0, 0], [0, 0, 0.5 * span],
+                       [6, 6, 6], area_samples)
     sc["bvh_max_depth"] = bvh_depth
     cam = _camera(width, height, 1.6, [0, -0.45, 1], [0, 1, 0], [0, 0.55 * span, -0.75 * span])
     return sc, cam
