@@ -317,25 +317,31 @@ def run_ours(args):
                "api": "yahr_b200_render (host buffers; kernel parameters up, RGB32F frame down to pinned memory)",
                "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
     else:
-        host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+        # every rank renders its own tile rows through the host-buffer shard entry and copies them into ONE pinned
+        # host frame shared by the ranks (POSIX shared memory): N PCIe links, no inter-GPU exchange
+        from yahr_b200.dist import SharedHostFrame
+        host = SharedHostFrame(w, h, rank, world, barrier=barrier)
         times = []
+        ste = None
         for i in range(args.warmup + args.steps):
             flush.zero_()
             barrier()
             t = time.perf_counter()
-            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
-            if rank == 0:
-                host_rgb.copy_(R.frame, non_blocking=True)
+            ste = R.scene.render_shard(cam, rank, world, (host.array, None), recursion_depth=args.depth, spp=args.spp)
             barrier()
             if i >= args.warmup:
                 times.append(time.perf_counter() - t)
         tt = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        bytes_t = torch.tensor([float(ste["h2d_bytes"]), float(ste["d2h_bytes"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(bytes_t)
         e2e_ms = float(tt) * 1e3
         e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": 256, "d2h_bytes_per_step": int(w * h * 12),
-               "api": "TileShardedRenderer.render (%s exchange) + frame down to pinned memory on rank 0" % R.mode,
+               "h2d_bytes_per_step": int(bytes_t[0]), "d2h_bytes_per_step": int(bytes_t[1]),
+               "api": "yahr_b200_render_shard on every rank (tile rows r mod N == rank) into one shared pinned host frame"
+                      + ("" if host.pinned else " (cudaHostRegister failed: pageable)"),
                "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
+        host.close()
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
     peak, peak_src = peaks()

@@ -178,6 +178,15 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
 int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
                             float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats);
 
+/* Multi-GPU host-buffer entry.  The frame is cut into whole rows of the reference's tile grid (squareBatches,
+ * Sampling.hs:5-21); this call renders rows shard_index, shard_index + shard_count, ... on the scene's GPU and
+ * copies exactly those pixel rows into rgb_out / primid_out, which are FULL-frame buffers (W*H*3 floats, W*H
+ * uint32), typically one pinned allocation shared by all shards.  The host runs one call per GPU concurrently (one
+ * thread or process each, each with its own yahr_scene on its own device), so every GPU uses its own PCIe link and
+ * no inter-GPU exchange is needed.  shard_count = 1 is yahr_b200_render. */
+int yahr_b200_render_shard(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                           int shard_index, int shard_count, float* rgb_out, uint32_t* primid_out, yahr_stats* stats);
+
 /* Same frame with the reference's output stage applied on the GPU: JuicyPixels' ImageRGBF -> 8-bit
  * conversion used by savePngImage (main.hs:142), truncate (255 * max 0 (min 1 x)), no gamma.
  * rgb8_out: W*H*3 bytes, row-major, row 0 = top.  Only a quarter of the bytes cross PCIe. */

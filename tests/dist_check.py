@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from yahr_b200 import api, scenes  # noqa: E402
-from yahr_b200.dist import TileShardedRenderer  # noqa: E402
+from yahr_b200.dist import SharedHostFrame, TileShardedRenderer  # noqa: E402
 
 
 def main():
@@ -51,6 +51,25 @@ def main():
                 ok = ok and same_rgb and same_pid
             R.close()
             dist.barrier()
+        # host-buffer multi-GPU entry: every rank copies its own tile rows into one shared pinned host frame
+        def barrier():
+            torch.cuda.synchronize()
+            dist.barrier()
+        host = SharedHostFrame(w, h, rank, world, barrier=barrier)
+        if rank == 0:
+            host.array[...] = np.nan
+        barrier()
+        s = api.Scene(sc)
+        for _ in range(2):
+            s.render_shard(cam, rank, world, (host.array, None))
+        s.close()
+        barrier()
+        if rank == 0:
+            same = np.array_equal(host.array.view(np.uint32), ref[0].cpu().numpy().view(np.uint32))
+            print("%s world=%d host shards rgb bit-equal=%s pinned=%s" % (name, world, same, host.pinned), flush=True)
+            ok = ok and same
+        barrier()
+        host.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

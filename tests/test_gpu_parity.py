@@ -254,6 +254,27 @@ def test_tile_sharding_partitions_the_image():
     s.close()
 
 
+def test_host_buffer_shards_assemble_the_frame():
+    """yahr_b200_render_shard: the row shards of G GPUs written into one host frame equal the single call."""
+    sc, cam = scenes.c2_bunny_proxy(384, 216, nu=40, nv=20)
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    full, fpid, fst = s.render(cam)
+    for G in (1, 2, 3, 8, 64):
+        rgb = np.full((h, w, 3), np.nan, np.float32)
+        pid = np.full((h, w), 0xABCDEF01, np.uint32)
+        rays = 0
+        for k in range(G):
+            st = s.render_shard(cam, k, G, (rgb, pid))
+            rays += st["n_primary"]
+        assert rays == w * h
+        assert np.array_equal(pid, fpid)
+        assert np.array_equal(rgb.view(np.uint32), full.view(np.uint32))
+    with pytest.raises(api.YahrError):
+        s.render_shard(cam, 2, 2, (rgb, pid))
+    s.close()
+
+
 def test_full_size_c4_terrain_properties_and_sampled_oracle():
     """BASELINE config C4 (1M triangles, 3840x2160): determinism, and oracle parity on every
     64th tile of the full-size frame."""

@@ -256,6 +256,22 @@ class Scene:
                                       pid.ctypes.data if pid is not None else None, C.byref(st)))
         return rgb, pid, st.as_dict()
 
+    def render_shard(self, cam, shard_index, shard_count, out, recursion_depth=1, spp=1, seed=0):
+        """yahr_b200_render_shard: renders the tile rows shard_index, shard_index + shard_count, ... into the
+        full-frame host buffers out = (rgb [H,W,3] float32, primid [H,W] uint32 or None)."""
+        c = make_camera(cam)
+        rgb, pid = out
+        st = Stats()
+        L = lib()
+        L.yahr_b200_render_shard.restype = C.c_int
+        L.yahr_b200_render_shard.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        _check(L.yahr_b200_render_shard(self._h, C.byref(c), recursion_depth, spp, seed, shard_index, shard_count,
+                                        rgb.ctypes.data if hasattr(rgb, "ctypes") else int(rgb),
+                                        (pid.ctypes.data if hasattr(pid, "ctypes") else int(pid)) if pid is not None else None,
+                                        C.byref(st)))
+        return st.as_dict()
+
     def download_bvh(self):
         """(order[n_prims], nodes[n_nodes,16] float32 raw, multi[n_multi,2], root_ref, root_box[6])."""
         i = self.info()

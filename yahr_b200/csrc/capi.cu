@@ -70,6 +70,10 @@ struct TileSet {
   std::vector<int4> hostTiles;        // windows, batch order (row-major over the tile grid)
   std::vector<uint32_t> hostStart;    // n + 1 prefix sums of the tile pixel counts
   uint32_t gridNx = 0;                // tiles per tile-row when the set is the whole image (stride 1)
+  // sets made of whole tile ROWS (stride / offset count rows of the tile grid): first tile of every owned row
+  // (+ end) and the pixel rows [y0, y1) it covers
+  std::vector<uint32_t> rowFirst;
+  std::vector<int2> rowY;
 };
 
 }  // namespace
@@ -89,7 +93,7 @@ struct yahr_scene {
   uint32_t* d_order = nullptr;            // primitive ID per DFS position (inspection)
   yahr_scene_info info{};
   // per (width, height, stride, offset) tile lists, uploaded once
-  std::map<std::tuple<int, int, int, int>, TileSet> tiles;
+  std::map<std::tuple<int, int, int, int, int>, TileSet> tiles;
   // wavefront scratch (grown on demand): hit records, shadow queue, work counters, spp buffers
   // two slots so that consecutive bands of the host-buffer entry can be in flight on two streams
   float4 *wfQ0[2] = {nullptr, nullptr}, *wfQ1[2] = {nullptr, nullptr}, *wfQ2[2] = {nullptr, nullptr};
@@ -134,8 +138,8 @@ struct yahr_loaded_scene {
 
 namespace {
 
-const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
-  auto key = std::make_tuple(w, h, stride, offset);
+const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, int byRows = 0) {
+  auto key = std::make_tuple(w, h, stride, offset, byRows);
   auto it = sc->tiles.find(key);
   if (it != sc->tiles.end()) return it->second;
   // samplePoints = squareBatches width height nBatches (main.hs:128-131).  numThreads only enters
@@ -144,23 +148,39 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset) {
   const int64_t nBatches = numBatches(1, w, h);
   std::vector<int4> host;
   std::vector<uint32_t> start(1, 0u);
-  for (int64_t b = offset; b < nBatches; b += stride) {
-    TileWindow t = batchWindow(w, h, b, nBatches);
-    if (t.x1 > t.x0 && t.y1 > t.y0) {
-      host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
-      start.push_back(start.back() + (uint32_t)((t.x1 - t.x0) * (t.y1 - t.y0)));
-    }
-  }
   TileSet ts;
+  int64_t gnx = nBatches, gny = 1;                     // (nx, ny) = loop count 1   (Sampling.hs:11-15)
+  while (gnx % 2 == 0 && 2 * (int64_t)w * gny < (int64_t)h * gnx) { gnx /= 2; gny *= 2; }
+  if (!byRows) {
+    for (int64_t b = offset; b < nBatches; b += stride) {
+      TileWindow t = batchWindow(w, h, b, nBatches);
+      if (t.x1 > t.x0 && t.y1 > t.y0) {
+        host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
+        start.push_back(start.back() + (uint32_t)((t.x1 - t.x0) * (t.y1 - t.y0)));
+      }
+    }
+  } else {
+    // tile `num` sits in row num `quot` nx of the grid (Sampling.hs:16); rows offset, offset + stride, ...
+    for (int64_t j = offset; j < gny; j += stride) {
+      const uint32_t firstOfRow = (uint32_t)host.size();
+      int y0 = 0, y1 = 0;
+      for (int64_t i = 0; i < gnx; ++i) {
+        TileWindow t = batchWindow(w, h, j * gnx + i, nBatches);
+        if (t.x1 > t.x0 && t.y1 > t.y0) {
+          host.push_back(make_int4(t.x0, t.y0, t.x1, t.y1));
+          start.push_back(start.back() + (uint32_t)((t.x1 - t.x0) * (t.y1 - t.y0)));
+          y0 = t.y0; y1 = t.y1;
+        }
+      }
+      if (host.size() > firstOfRow) { ts.rowFirst.push_back(firstOfRow); ts.rowY.push_back(make_int2(y0, y1)); }
+    }
+    ts.rowFirst.push_back((uint32_t)host.size());
+  }
   ts.n = (uint32_t)host.size();
   ts.nItems = start.back();
   ts.hostTiles = host;
   ts.hostStart = start;
-  if (stride == 1) {                                   // (nx, ny) = loop count 1   (Sampling.hs:11-15)
-    int64_t nx = nBatches, ny = 1;
-    while (nx % 2 == 0 && 2 * (int64_t)w * ny < (int64_t)h * nx) { nx /= 2; ny *= 2; }
-    ts.gridNx = (ts.n == (uint32_t)nBatches) ? (uint32_t)nx : 0;   // 0 when empty windows were dropped
-  }
+  if (stride == 1) ts.gridNx = (ts.n == (uint32_t)nBatches) ? (uint32_t)gnx : 0;   // 0 when empty windows were dropped
   uint64_t bytes = 0;
   ts.d_tiles = devUpload(host, bytes);
   ts.d_tileStart = devUpload(start, bytes);
@@ -204,7 +224,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
   if (opts->kernel == 2 && opts->recursion_depth != 1)
     return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
 
-  const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset);
+  // reserved[1] = 1: tile_stride / tile_offset count whole ROWS of the tile grid (host-buffer shards)
+  const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset, opts->reserved[1] == 1 ? 1 : 0);
   plan.ts = &ts;
   RenderParams& P = plan.P;
   P.sc = sc->dev;
@@ -686,13 +707,18 @@ int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yah
 }
 
 static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
-                      float* rgb_out, unsigned char* rgb8_out, uint32_t* primid_out, yahr_stats* stats) {
+                      float* rgb_out, unsigned char* rgb8_out, uint32_t* primid_out, yahr_stats* stats,
+                      int shardIndex = 0, int shardCount = 1) {
   if (!scene || !cam || (!rgb_out && !rgb8_out)) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
   try {
     const double w0 = nowMs();
     yahr_render_opts o{};
     o.recursion_depth = recursion_depth; o.spp = spp; o.seed = seed;
-    o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = 1; o.tile_offset = 0;
+    if (shardCount < 1 || shardIndex < 0 || shardIndex >= shardCount)
+      return fail(YAHR_ERR_INVALID_ARGUMENT, "shard_index / shard_count invalid");
+    // the frame is cut into whole rows of the reference's tile grid; this call renders rows shardIndex,
+    // shardIndex + shardCount, ... (all of them for the single-GPU entry)
+    o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = shardCount; o.tile_offset = shardIndex; o.reserved[1] = 1;
     {
       CameraSetup cs;
       std::string err;
@@ -724,19 +750,19 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     // on a caller stream
     CU(cudaDeviceSynchronize());
 
-    // The frame is rendered in horizontal BANDS of whole tile rows (tiles are numbered row-major over
-    // the tile grid, Sampling.hs:16), and every finished band is copied to the caller's buffer on a
-    // copy stream while later bands render, so the device-to-host transfer overlaps traversal.  Bands
-    // alternate between two render streams (each with its own shadow queue), so the shadow trace of one
-    // band overlaps the primary trace of the next and the tails of the persistent kernels are filled.
+    // The rows of this call are rendered in BANDS of consecutive owned tile rows, and every finished band is copied
+    // to the caller's buffer on a copy stream while later bands render, so the device-to-host transfer overlaps
+    // traversal.  Bands alternate between two render streams (each with its own shadow queue), so the shadow trace
+    // of one band overlaps the primary trace of the next and the tails of the persistent kernels are filled.
     // spp > 1 accumulates per pixel across sample passes inside a band, which works the same way.
+    const uint32_t nRows = (uint32_t)ts.rowY.size();
     uint32_t nBands = 1;
-    const uint32_t tileRows = ts.gridNx ? ts.n / ts.gridNx : 0;
-    if (tileRows >= 2) {
+    if (nRows >= 2) {
       const char* env = getenv("YAHR_B200_BANDS");
       uint32_t want = env ? (uint32_t)atoi(env) : 8u;
+      if (shardCount > 1 && !env) want = (8u + (uint32_t)shardCount - 1u) / (uint32_t)shardCount + 1u;   // smaller shards, fewer bands
       if (want < 1) want = 1;
-      nBands = want < tileRows ? want : tileRows;
+      nBands = want < nRows ? want : nRows;
     }
     while (scene->bandEvents.size() < nBands) {
       cudaEvent_t e;
@@ -748,40 +774,50 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     CU(cudaEventRecord(scene->ev0, rs));
     if (nBands > 1) CU(cudaStreamWaitEvent(rs1, scene->ev0, 0));     // counters are cleared before any band
     uint64_t d2h = 0;
-    for (uint32_t b = 0; b < nBands; ++b) {
-      uint32_t first = 0, count = ts.n;
-      int y0 = 0, y1 = H_;
-      if (nBands > 1) {
-        const uint32_t r0 = (uint32_t)((uint64_t)tileRows * b / nBands), r1 = (uint32_t)((uint64_t)tileRows * (b + 1) / nBands);
-        first = r0 * ts.gridNx; count = (r1 - r0) * ts.gridNx;
-        y0 = ts.hostTiles[first].y; y1 = ts.hostTiles[first + count - 1].w;
-      }
+    for (uint32_t b = 0; b < nBands && nRows; ++b) {
+      const uint32_t r0 = (uint32_t)((uint64_t)nRows * b / nBands), r1 = (uint32_t)((uint64_t)nRows * (b + 1) / nBands);
+      const uint32_t first = ts.rowFirst[r0], count = ts.rowFirst[r1] - ts.rowFirst[r0];
       cudaStream_t bs = (b & 1u) ? rs1 : rs;
       enqueueTiles(scene, plan, first, count, bs, &launches, (b == 0) ? scene->phaseEv : nullptr, (int)(b & 1u));
-      if (rgb8_out) {                                   // output stage on the GPU: 1 byte per channel goes down
-        const size_t rowElems = (size_t)W_ * 3;
-        CU(launchQuantizeRgb8(scene->d_rgb, scene->d_rgb8, (size_t)y0 * rowElems, (size_t)(y1 - y0) * rowElems, bs,
-                              &launches));
+      // copies: one per run of pixel rows that is contiguous in the frame (the whole band when every row is owned)
+      uint32_t r = r0;
+      while (r < r1) {
+        uint32_t e = r + 1;
+        while (e < r1 && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+        const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
+        if (rgb8_out) {                                   // output stage on the GPU: 1 byte per channel goes down
+          const size_t rowElems = (size_t)W_ * 3;
+          CU(launchQuantizeRgb8(scene->d_rgb, scene->d_rgb8, (size_t)y0 * rowElems, (size_t)(y1 - y0) * rowElems, bs,
+                                &launches));
+        }
+        r = e;
       }
       CU(cudaEventRecord(scene->bandEvents[b], bs));
       CU(cudaStreamWaitEvent(cp, scene->bandEvents[b], 0));
-      if (rgb_out) {
-        const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
-        CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
-                           (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
-        d2h += (uint64_t)(y1 - y0) * rowBytes;
-      }
-      if (rgb8_out) {
-        const size_t rowBytes = (size_t)W_ * 3;
-        CU(cudaMemcpyAsync(rgb8_out + (size_t)y0 * rowBytes, scene->d_rgb8 + (size_t)y0 * rowBytes,
-                           (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
-        d2h += (uint64_t)(y1 - y0) * rowBytes;
-      }
-      if (primid_out) {
-        const size_t idBytes = (size_t)W_ * sizeof(uint32_t);
-        CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
-                           (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
-        d2h += (uint64_t)(y1 - y0) * idBytes;
+      r = r0;
+      while (r < r1) {
+        uint32_t e = r + 1;
+        while (e < r1 && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+        const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
+        if (rgb_out) {
+          const size_t rowBytes = (size_t)W_ * 3 * sizeof(float);
+          CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
+                             (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+          d2h += (uint64_t)(y1 - y0) * rowBytes;
+        }
+        if (rgb8_out) {
+          const size_t rowBytes = (size_t)W_ * 3;
+          CU(cudaMemcpyAsync(rgb8_out + (size_t)y0 * rowBytes, scene->d_rgb8 + (size_t)y0 * rowBytes,
+                             (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+          d2h += (uint64_t)(y1 - y0) * rowBytes;
+        }
+        if (primid_out) {
+          const size_t idBytes = (size_t)W_ * sizeof(uint32_t);
+          CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
+                             (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
+          d2h += (uint64_t)(y1 - y0) * idBytes;
+        }
+        r = e;
       }
     }
     if (nBands > 1) {                                  // join: the last band of each render stream
@@ -824,6 +860,12 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
                      float* rgb_out, uint32_t* primid_out, yahr_stats* stats) {
   if (!rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb_out is NULL");
   return renderHost(scene, cam, recursion_depth, spp, seed, rgb_out, nullptr, primid_out, stats);
+}
+
+int yahr_b200_render_shard(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                           int shard_index, int shard_count, float* rgb_out, uint32_t* primid_out, yahr_stats* stats) {
+  if (!rgb_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb_out is NULL");
+  return renderHost(scene, cam, recursion_depth, spp, seed, rgb_out, nullptr, primid_out, stats, shard_index, shard_count);
 }
 
 int yahr_b200_render_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,

@@ -141,6 +141,54 @@ class TileShardedRenderer:
         self.scene.close()
 
 
+class SharedHostFrame:
+    """One pinned host frame (H x W x 3 float32) shared by the per-GPU processes of a node, for the host-buffer
+    multi-GPU entry (yahr_b200_render_shard): every rank copies its own tile rows into it over its own PCIe link,
+    so the frame reaches host memory without any inter-GPU exchange.  POSIX shared memory, page-locked in every
+    process with cudaHostRegister."""
+
+    def __init__(self, width, height, rank, world, name=None, barrier=None):
+        import os
+        from multiprocessing import shared_memory
+        self.rank, self.world = rank, world
+        self.nbytes = int(width) * int(height) * 12
+        name = name or ("yahr_b200_frame_%s" % os.environ.get("MASTER_PORT", "0"))
+        self._owner = rank == 0
+        if self._owner:
+            try:
+                stale = shared_memory.SharedMemory(name=name)
+                stale.close()
+                stale.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.nbytes)
+        if barrier:
+            barrier()
+        if not self._owner:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.array = np.ndarray((int(height), int(width), 3), np.float32, buffer=self.shm.buf)
+        import torch
+        rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+        self.pinned = int(rc) == 0
+        if barrier:
+            barrier()
+
+    def close(self):
+        import torch
+        if getattr(self, "shm", None) is None:
+            return
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+        self.array = None
+        self.shm.close()
+        if self._owner:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+        self.shm = None
+
+
 def gather_tiles_reference(width, height, world_size, per_rank_frames):
     """Host-side statement of what the exchange must produce (used by the gloo CPU tests):
     pixel (u, v) comes from the rank that owns its tile."""
