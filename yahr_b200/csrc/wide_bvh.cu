@@ -139,7 +139,7 @@ inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + pe
     cudaError_t e__ = (call);                                                               \
     if (e__ != cudaSuccess) {                                                               \
       out.error = e__; out.where = #call;                                                   \
-      cudaFree(mark); cudaFree(flags); cudaFree(scan); cudaFree(temp); cudaFree(need);      \
+      if (arena) cudaFreeAsync(arena, st);                                                  \
       cudaFree(out.wide);                                                                   \
       out.wide = nullptr;                                                                   \
       return false;                                                                         \
@@ -149,19 +149,24 @@ inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + pe
 bool buildWideOnDevice(const float4* flat, uint32_t nInner, uint32_t binaryDepth, WideBuildOutput& out) {
   out = WideBuildOutput();
   if (nInner == 0 || !flat) return true;              // the root is a leaf (or the scene is empty): nothing to collapse
-  uint32_t *mark = nullptr, *flags = nullptr, *scan = nullptr, *need = nullptr;
-  void* temp = nullptr;
-  size_t tempBytes = 0;
   cudaStream_t st = nullptr;
-  WB(cudaMalloc(&mark, (size_t)nInner * sizeof(uint32_t)));
-  WB(cudaMalloc(&flags, ((size_t)nInner + 1) * sizeof(uint32_t)));
-  WB(cudaMalloc(&scan, ((size_t)nInner + 1) * sizeof(uint32_t)));
-  WB(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, flags, scan, (int)(nInner + 1), st));
-  WB(cudaMalloc(&temp, tempBytes ? tempBytes : 1));
+  char* arena = nullptr;
+  // temporaries come from one stream-ordered allocation (the pool keeps its memory between builds)
+  size_t tempBytes = 0;
+  WB(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(nInner + 1), st));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t words = align(((size_t)nInner + 1) * sizeof(uint32_t));
+  const size_t total = 4 * words + align(tempBytes ? tempBytes : 1);
+  WB(cudaMallocAsync((void**)&arena, total, st));
+  uint32_t* mark = reinterpret_cast<uint32_t*>(arena);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(arena + words);
+  uint32_t* scan = reinterpret_cast<uint32_t*>(arena + 2 * words);
+  uint32_t* need = reinterpret_cast<uint32_t*>(arena + 3 * words);       // nWide <= nInner entries
+  void* temp = arena + 4 * words;
   WB(cudaMemsetAsync(mark, 0, (size_t)nInner * sizeof(uint32_t), st));
   const uint32_t one = 1u;
   WB(cudaMemcpyAsync(mark, &one, sizeof(one), cudaMemcpyHostToDevice, st));     // the root (pre-order index 0)
-  // every wave descends at least one binary level, so binaryDepth + 1 waves reach every node
+  // every wave descends at least one binary level, so binaryDepth + 2 waves reach every node
   const uint32_t nWaves = binaryDepth + 2u;
   for (uint32_t wave = 1; wave <= nWaves; ++wave)
     k_wide_mark<<<blocks(nInner), 256, 0, st>>>(flat, nInner, mark, wave);
@@ -173,7 +178,6 @@ bool buildWideOnDevice(const float4* flat, uint32_t nInner, uint32_t binaryDepth
   WB(cudaGetLastError());
   WB(cudaMalloc(&out.wide, (size_t)(nWide ? nWide : 1) * kWideNodeVec * sizeof(float4)));
   k_wide_emit<<<blocks(nInner), 256, 0, st>>>(flat, nInner, mark, scan, out.wide);
-  WB(cudaMalloc(&need, (size_t)(nWide ? nWide : 1) * sizeof(uint32_t)));
   for (uint32_t wave = nWaves + 1u; wave >= 1u; --wave)
     k_wide_need<<<blocks(nInner), 256, 0, st>>>(out.wide, nInner, mark, scan, wave, need);
   uint32_t rootNeed = 0;
@@ -182,7 +186,7 @@ bool buildWideOnDevice(const float4* flat, uint32_t nInner, uint32_t binaryDepth
   WB(cudaGetLastError());
   out.nWide = nWide;
   out.stackNeed = rootNeed;
-  cudaFree(mark); cudaFree(flags); cudaFree(scan); cudaFree(temp); cudaFree(need);
+  cudaFreeAsync(arena, st);
   return true;
 }
 
