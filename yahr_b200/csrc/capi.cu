@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libyahr_b200.so (include/yahr_b200.h).  No CPU fallback: every compute
 // entry point needs a CUDA device and fails with YAHR_ERR_NO_DEVICE / YAHR_ERR_CUDA otherwise.
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -764,11 +765,15 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       if (want < 1) want = 1;
       nBands = want < nRows ? want : nRows;
     }
+    static const bool timeline = getenv("YAHR_B200_TIMELINE") != nullptr;     // debug: per-band completion times on stderr
     while (scene->bandEvents.size() < nBands) {
       cudaEvent_t e;
-      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e, timeline ? cudaEventDefault : cudaEventDisableTiming));
       scene->bandEvents.push_back(e);
     }
+    std::vector<cudaEvent_t> copyDone;
+    if (timeline)
+      for (uint32_t b = 0; b < nBands; ++b) { cudaEvent_t e; CU(cudaEventCreate(&e)); copyDone.push_back(e); }
     uint32_t launches = 0;
     CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
     CU(cudaEventRecord(scene->ev0, rs));
@@ -819,6 +824,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         }
         r = e;
       }
+      if (timeline) CU(cudaEventRecord(copyDone[b], cp));
     }
     if (nBands > 1) {                                  // join: the last band of each render stream
       CU(cudaStreamWaitEvent(rs, scene->bandEvents[nBands - 1], 0));
@@ -829,6 +835,17 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
     CU(cudaStreamSynchronize(rs));
     CU(cudaStreamSynchronize(cp));
+    if (timeline && nRows) {
+      fprintf(stderr, "[yahr_b200 timeline] wall %.3f ms;", nowMs() - w0);
+      for (uint32_t b = 0; b < nBands; ++b) {
+        float tr = 0, tc = 0;
+        cudaEventElapsedTime(&tr, scene->ev0, scene->bandEvents[b]);
+        cudaEventElapsedTime(&tc, scene->ev0, copyDone[b]);
+        fprintf(stderr, " band %u render %.3f copy %.3f;", b, tr, tc);
+      }
+      fprintf(stderr, "\n");
+      for (auto e : copyDone) cudaEventDestroy(e);
+    }
     if (stats) {
       std::memset(stats, 0, sizeof(*stats));
       float ms = 0;
