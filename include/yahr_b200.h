@@ -178,6 +178,15 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
 int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
                             float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats);
 
+/* Multi-GPU device-buffer entry.  Renders the rows shard_index, shard_index + shard_count, ... of the reference's
+ * tile grid into the LOCAL buffers (full-frame sized, on the scene's GPU), then pushes exactly those pixel rows into
+ * the gather buffers with device-to-device copies enqueued on `stream` (the gather frame usually lives on rank 0 and
+ * is mapped here with yahr_b200_ipc_open: a few large NVLink transfers per frame).  gather == local or NULL: no push.
+ * opts->tile_stride / tile_offset are ignored.  Returns after enqueueing unless `stats` is non-NULL. */
+int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
+                                  int shard_index, int shard_count, float* d_rgb_local, float* d_rgb_gather,
+                                  uint32_t* d_primid_local, uint32_t* d_primid_gather, void* stream, yahr_stats* stats);
+
 /* Multi-GPU host-buffer entry.  The frame is cut into whole rows of the reference's tile grid (squareBatches,
  * Sampling.hs:5-21); this call renders rows shard_index, shard_index + shard_count, ... on the scene's GPU and
  * copies exactly those pixel rows into rgb_out / primid_out, which are FULL-frame buffers (W*H*3 floats, W*H

@@ -37,7 +37,7 @@ def main():
             s.render_device(cam, full.data_ptr(), fpid.data_ptr())
             s.close()
             ref = (full, fpid)
-        for mode in ("p2p", "reduce"):
+        for mode in ("rows", "p2p", "reduce"):
             R = TileShardedRenderer(sc, cam, mode=mode, want_primid=True)
             for _ in range(3):
                 R.render()

@@ -84,3 +84,16 @@ def test_rank_tiles_partition():
             seen = sorted(t for r in range(world) for t in tiles.rank_tiles(w, h, world, r))
             assert seen == list(range(n))
             assert sum(tiles.rank_pixel_count(w, h, world, r) for r in range(world)) == w * h
+
+
+def test_rank_rows_partition():
+    """Row sharding: every pixel row belongs to exactly one rank, rows of a rank are whole tile rows."""
+    api.build_library()
+    for (w, h) in [(512, 512), (1920, 1080), (3840, 2160), (37, 11), (5, 300)]:
+        for world in (1, 2, 3, 8):
+            owner = np.full(h, -1)
+            for r in range(world):
+                for (_, y0, y1) in tiles.rank_rows(w, h, world, r):
+                    assert (owner[y0:y1] == -1).all()
+                    owner[y0:y1] = r
+            assert (owner >= 0).all()

@@ -312,7 +312,7 @@ class Scene:
 
     def render_device(self, cam, d_rgb, d_primid=None, recursion_depth=1, spp=1, seed=0,
                       traversal=TRAVERSAL_REFERENCE, tile_stride=1, tile_offset=0, stream=None, stats=True,
-                      kernel=0, tune=0):
+                      kernel=0, tune=0, by_rows=False):
         """Device-buffer entry (yahr_b200_render_device).  d_rgb / d_primid are raw device pointers
         (ints), e.g. torch_tensor.data_ptr().  Returns a stats dict (synchronises) or None."""
         c = make_camera(cam)
@@ -320,12 +320,39 @@ class Scene:
         o.recursion_depth, o.spp, o.seed = recursion_depth, spp, seed
         o.traversal, o.tile_stride, o.tile_offset, o.kernel = traversal, tile_stride, tile_offset, kernel
         o.reserved[0] = tune
+        o.reserved[1] = 1 if by_rows else 0     # tile_stride / tile_offset count whole rows of the tile grid
         st = Stats() if stats else None
         _check(lib().yahr_b200_render_device(self._h, C.byref(c), C.byref(o), C.c_void_p(d_rgb),
                                              C.c_void_p(d_primid) if d_primid else None,
                                              C.c_void_p(stream) if stream else None,
                                              C.byref(st) if stats else None))
         return st.as_dict() if stats else None
+
+
+def _ptr(x):
+    return C.c_void_p(x) if x else None
+
+
+def render_device_shard(scene, cam, shard_index, shard_count, d_rgb_local, d_rgb_gather=None, d_primid_local=None,
+                        d_primid_gather=None, recursion_depth=1, spp=1, seed=0, traversal=TRAVERSAL_REFERENCE,
+                        stream=None, stats=False, kernel=0, tune=0):
+    """yahr_b200_render_device_shard: this shard's tile rows into the local buffers, then pushed into the gather
+    buffers (raw device pointers, possibly peer memory) with device-to-device copies on `stream`."""
+    c = make_camera(cam)
+    o = RenderOpts()
+    o.recursion_depth, o.spp, o.seed = recursion_depth, spp, seed
+    o.traversal, o.tile_stride, o.tile_offset, o.kernel = traversal, 1, 0, kernel
+    o.reserved[0] = tune
+    st = Stats() if stats else None
+    L = lib()
+    L.yahr_b200_render_device_shard.restype = C.c_int
+    L.yahr_b200_render_device_shard.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.POINTER(Stats)]
+    _check(L.yahr_b200_render_device_shard(scene._h, C.byref(c), C.byref(o), shard_index, shard_count, _ptr(d_rgb_local),
+                                           _ptr(d_rgb_gather), _ptr(d_primid_local), _ptr(d_primid_gather), _ptr(stream),
+                                           C.byref(st) if stats else None))
+    return st.as_dict() if stats else None
 
 
 class HostBvh:

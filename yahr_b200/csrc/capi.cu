@@ -707,6 +707,62 @@ int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yah
   }
 }
 
+// Device-buffer multi-GPU entry: render the tile rows of this shard into the LOCAL frame, then push exactly those
+// pixel rows into the gather frame (usually rank 0's, mapped with yahr_b200_ipc_open) with device-to-device copies on
+// the same stream: a few large NVLink transfers instead of one small remote store per pixel.
+int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts_in,
+                                  int shard_index, int shard_count, float* d_rgb_local, float* d_rgb_gather,
+                                  uint32_t* d_primid_local, uint32_t* d_primid_gather, void* stream, yahr_stats* stats) {
+  if (!scene || !cam || !opts_in || !d_rgb_local) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+    return fail(YAHR_ERR_INVALID_ARGUMENT, "shard_index / shard_count invalid");
+  try {
+    yahr_render_opts o = *opts_in;
+    o.tile_stride = shard_count; o.tile_offset = shard_index; o.reserved[1] = 1;      // whole rows of the tile grid
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = renderCommon(scene, cam, &o, d_rgb_local, d_primid_local, st, nullptr, false);
+    if (rc) return rc;
+    CameraSetup cs;
+    std::string err;
+    rc = setupCamera(cam, cs, err);
+    if (rc) return fail(rc, err);
+    const TileSet& ts = tilesFor(scene, cs.width, cs.height, shard_count, shard_index, 1);
+    const bool pushRgb = d_rgb_gather && d_rgb_gather != d_rgb_local;
+    const bool pushPid = d_primid_gather && d_primid_local && d_primid_gather != d_primid_local;
+    const uint32_t nRows = (uint32_t)ts.rowY.size();
+    uint32_t r = 0;
+    while ((pushRgb || pushPid) && r < nRows) {
+      uint32_t e = r + 1;
+      while (e < nRows && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+      const size_t y0 = (size_t)ts.rowY[r].x, y1 = (size_t)ts.rowY[e - 1].y;
+      if (pushRgb) {
+        const size_t rowBytes = (size_t)cs.width * 3 * sizeof(float);
+        CU(cudaMemcpyAsync((char*)d_rgb_gather + y0 * rowBytes, (const char*)d_rgb_local + y0 * rowBytes, (y1 - y0) * rowBytes,
+                           cudaMemcpyDeviceToDevice, st));
+      }
+      if (pushPid) {
+        const size_t rowBytes = (size_t)cs.width * sizeof(uint32_t);
+        CU(cudaMemcpyAsync((char*)d_primid_gather + y0 * rowBytes, (const char*)d_primid_local + y0 * rowBytes,
+                           (y1 - y0) * rowBytes, cudaMemcpyDeviceToDevice, st));
+      }
+      r = e;
+    }
+    if (stats) {
+      std::memset(stats, 0, sizeof(*stats));
+      CU(cudaStreamSynchronize(st));
+      unsigned long long c[3];
+      CU(cudaMemcpy(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+      stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
+      stats->tiles = ts.n;
+    }
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  } catch (const std::exception& e) {
+    return fail(YAHR_ERR_INTERNAL, e.what());
+  }
+}
+
 static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
                       float* rgb_out, unsigned char* rgb8_out, uint32_t* primid_out, yahr_stats* stats,
                       int shardIndex = 0, int shardCount = 1) {

@@ -23,3 +23,28 @@ def rank_tiles(width, height, world_size, rank, num_threads=1):
 def rank_pixel_count(width, height, world_size, rank):
     wins = tile_windows(width, height)
     return sum((x1 - x0) * (y1 - y0) for (x0, y0, x1, y1) in wins[rank::world_size])
+
+
+def tile_grid(width, height, num_threads=1):
+    """(nx, ny) of squareBatches' tile grid: (nx, ny) = loop count 1 (Sampling.hs:11-15); tile `num` sits in row
+    num // nx (Sampling.hs:16)."""
+    n = api.num_batches(num_threads, width, height)
+    nx, ny = n, 1
+    while nx % 2 == 0 and 2 * width * ny < height * nx:
+        nx //= 2
+        ny *= 2
+    return nx, ny
+
+
+def rank_rows(width, height, world_size, rank):
+    """Row sharding (the "rows" exchange and yahr_b200_render_shard): the tile rows rank `rank` renders and the
+    pixel rows [y0, y1) each covers.  Tile row r -> rank r mod G."""
+    nx, ny = tile_grid(width, height)
+    n = nx * ny
+    out = []
+    for r in range(rank, ny, world_size):
+        ys = [api.batch_window(width, height, r * nx + i, n) for i in range(nx)]
+        ys = [(y0, y1) for (x0, y0, x1, y1) in ys if x1 > x0 and y1 > y0]
+        if ys:
+            out.append((r, ys[0][0], ys[0][1]))
+    return out
