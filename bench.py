@@ -427,7 +427,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4-terrain")
     ap.add_argument("--traversal", default="reference", choices=["reference", "ordered"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "rows", "reduce"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "rows", "reduce"])
     ap.add_argument("--depth", type=int, default=1)
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--kernel", type=int, default=0)

@@ -730,8 +730,28 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
     const bool pushRgb = d_rgb_gather && d_rgb_gather != d_rgb_local;
     const bool pushPid = d_primid_gather && d_primid_local && d_primid_gather != d_primid_local;
     const uint32_t nRows = (uint32_t)ts.rowY.size();
+    // equally tall, equally spaced rows (the usual case: 2160 = 135 x 16): ONE strided copy per buffer
+    bool uniform = nRows >= 2;
+    for (uint32_t k = 1; uniform && k < nRows; ++k)
+      uniform = (ts.rowY[k].y - ts.rowY[k].x) == (ts.rowY[0].y - ts.rowY[0].x) &&
+                (ts.rowY[k].x - ts.rowY[k - 1].x) == (ts.rowY[1].x - ts.rowY[0].x);
+    if ((pushRgb || pushPid) && uniform) {
+      const size_t y0 = (size_t)ts.rowY[0].x, rowsTall = (size_t)(ts.rowY[0].y - ts.rowY[0].x);
+      const size_t spacing = (size_t)(ts.rowY[1].x - ts.rowY[0].x);
+      if (pushRgb) {
+        const size_t rowBytes = (size_t)cs.width * 3 * sizeof(float);
+        CU(cudaMemcpy2DAsync((char*)d_rgb_gather + y0 * rowBytes, spacing * rowBytes, (const char*)d_rgb_local + y0 * rowBytes,
+                             spacing * rowBytes, rowsTall * rowBytes, nRows, cudaMemcpyDeviceToDevice, st));
+      }
+      if (pushPid) {
+        const size_t rowBytes = (size_t)cs.width * sizeof(uint32_t);
+        CU(cudaMemcpy2DAsync((char*)d_primid_gather + y0 * rowBytes, spacing * rowBytes,
+                             (const char*)d_primid_local + y0 * rowBytes, spacing * rowBytes, rowsTall * rowBytes, nRows,
+                             cudaMemcpyDeviceToDevice, st));
+      }
+    }
     uint32_t r = 0;
-    while ((pushRgb || pushPid) && r < nRows) {
+    while ((pushRgb || pushPid) && !uniform && r < nRows) {
       uint32_t e = r + 1;
       while (e < nRows && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
       const size_t y0 = (size_t)ts.rowY[r].x, y1 = (size_t)ts.rowY[e - 1].y;

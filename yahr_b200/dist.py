@@ -5,14 +5,15 @@ strided over ranks (tile i -> rank i mod G, Sampling.hs:9-21).  The frame ends u
 The only exchange is at the end of a frame -- the reference's `concat` of per-tile sample lists
 (main.hs:83,95) -- and there are two ways to do it:
 
-  "p2p"    (default) tile i -> rank i mod G; rank 0's frame buffer is mapped into every rank through CUDA IPC and
+  "p2p"    tile i -> rank i mod G; rank 0's frame buffer is mapped into every rank through CUDA IPC and
            the render kernel stores each finished pixel straight into it over NVLink: the gather
            is fused into the kernel's epilogue and overlaps traversal.  A one-element NCCL
            all-reduce on the render stream is the completion fence.
   "rows"   the frame is cut into whole rows of the reference's tile grid, row r -> rank r mod G; every rank renders
            its rows into a local frame and pushes them into rank 0's frame (same IPC mapping) with a few large
-           device-to-device copies on the render stream, then the same fence.  Measured slower than "p2p" (the
-           copies run after the kernels instead of under them: 0.72 vs 0.64 ms at 4 GPUs on C4).
+           device-to-device copies (one strided 2-D copy when the rows are equally tall) on the render stream, then
+           the same fence.  The copies run after the kernels instead of under them, but they are bulk transfers.
+  "auto"   (default) "p2p" up to 5 GPUs, "rows" from 6 (C4: 4 GPUs p2p 0.64 / rows 0.74 ms, 8 GPUs 0.65 / 0.49 ms).
   "reduce" every rank renders into a zeroed local full frame and the frames are summed onto rank 0
            with one NCCL reduce -- exact, because every pixel has exactly one owner and x + 0 = x.
            This is the plain-library baseline.
@@ -26,12 +27,17 @@ from . import api
 
 
 class TileShardedRenderer:
-    def __init__(self, scene, cam, mode="p2p", want_primid=False, group=None):
+    def __init__(self, scene, cam, mode="auto", want_primid=False, group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if mode == "auto":
+            # peer stores overlap traversal but arrive at rank 0 as small writes and their volume ((G-1)/G of the frame,
+            # twice for lit pixels) does not shrink with G; bulk row pushes do, but run after the kernels.  Measured on C4:
+            # 4 GPUs p2p 0.64 / rows 0.74 ms, 8 GPUs p2p 0.65 / rows 0.49 ms.
+            mode = "rows" if self.world >= 6 else "p2p"
         self.group = group
         self.cam = cam
         self.width, self.height = api.image_size(cam)
