@@ -351,17 +351,18 @@ def run_ours(args):
         ste = None
         for i in range(args.warmup + args.steps):
             flush.zero_()
-            barrier()
+            barrier()                                  # ranks leave the barrier together: a common start
             t = time.perf_counter()
             ste = R.scene.render_shard(cam, rank, world, (host.array, None), recursion_depth=args.depth, spp=args.spp)
-            barrier()
+            dt = time.perf_counter() - t               # the call returns when this rank's rows are in the host frame
             if i >= args.warmup:
-                times.append(time.perf_counter() - t)
-        tt = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+                times.append(dt)
+        # a frame is complete when the slowest rank's call has returned: max over ranks, per step
+        tt = torch.tensor(times, dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         bytes_t = torch.tensor([float(ste["h2d_bytes"]), float(ste["d2h_bytes"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(bytes_t)
-        e2e_ms = float(tt) * 1e3
+        e2e_ms = float(tt.mean()) * 1e3
         e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(bytes_t[0]), "d2h_bytes_per_step": int(bytes_t[1]),
                "api": "yahr_b200_render_shard on every rank (tile rows r mod N == rank) into one shared pinned host frame"
