@@ -317,6 +317,33 @@ def test_full_size_c4_terrain_properties_and_sampled_oracle():
     assert (np.sqrt((d ** 2).mean(axis=0)) <= RMSE).all()
 
 
+@pytest.mark.parametrize("area", [False, True])
+def test_full_size_c5_sampled_oracle(area):
+    """BASELINE config C5 (144 bunny copies, 10 M triangles, BVH 40, 3840x2160): oracle parity on every 256th tile of
+    the full-size frame; with the area light + 2 spp (both extensions) as the config names them."""
+    sc, cam = scenes.c5_replicated_bunny(area_samples=1 if area else 0)
+    spp = 2 if area else 1
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    info = s.info()
+    assert info["n_primitives"] == 10_017_218 and info["n_wide_nodes"] > 0
+    rgb, pid, st = s.render(cam, spp=spp, seed=77)
+    s.close()
+    assert st["n_primary"] == spp * w * h
+    o = ob.OracleScene(sc)
+    orgb = np.full((h, w, 3), np.nan, np.float32)
+    opid = np.full((h, w), 0xFFFFFFFE, np.uint32)
+    ot = np.zeros((h, w), np.float32)
+    o.render(cam, spp=spp, seed=77, tile_stride=256, tile_offset=7, out=(orgb, opid, ot))
+    o.close()
+    sel = opid != 0xFFFFFFFE
+    assert sel.sum() > 30000
+    assert np.array_equal(pid[sel], opid[sel])
+    d = (rgb[sel].astype(np.float64) - orgb[sel].astype(np.float64))
+    assert np.abs(d).max() <= MAX_ABS
+    assert (np.sqrt((d ** 2).mean(axis=0)) <= RMSE).all()
+
+
 def test_empty_scene_renders_black():
     sc = scenes._empty_scene()
     cam = scenes._camera(64, 48, 1.0, [0, 0, 1], [0, 1, 0], [0, 0, 0])
