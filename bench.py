@@ -285,6 +285,14 @@ def run_ours(args):
             R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             ev[i][1].record()
         barrier()
+        # the timed region lasts only a few milliseconds (nvidia-smi samples every 200 ms): keep the same load up for
+        # ~0.8 s more, untimed, so that the clock / throttle samples are taken under this very workload
+        t_load = time.time()
+        while time.time() - t_load < 0.8:
+            for _ in range(20):
+                R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
+            torch.cuda.synchronize()
+        barrier()
         # kernel-only time of the dominant kernel, measured live with CUDA events (library stats)
         for i in range(min(args.steps, 5)):
             flush.zero_()
