@@ -286,9 +286,9 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         # the timed region lasts only a few milliseconds (nvidia-smi samples every 200 ms): keep the same load up for
-        # ~0.8 s more, untimed, so that the clock / throttle samples are taken under this very workload
-        t_load = time.time()
-        while time.time() - t_load < 0.8:
+        # 500 more frames, untimed, so that the clock / throttle samples are taken under this very workload
+        # (a fixed frame count, the same on every rank: the exchange contains a collective)
+        for _ in range(25):
             for _ in range(20):
                 R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             torch.cuda.synchronize()
