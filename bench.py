@@ -286,12 +286,17 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         # the timed region lasts only a few milliseconds (nvidia-smi samples every 200 ms): keep the same load up for
-        # 500 more frames, untimed, so that the clock / throttle samples are taken under this very workload
-        # (a fixed frame count, the same on every rank: the exchange contains a collective)
-        for _ in range(25):
-            for _ in range(20):
-                R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
-            torch.cuda.synchronize()
+        # about 0.8 s more (at most 500 frames), untimed, so that the clock / throttle samples are taken under this very workload
+        # (the frame count is derived from the max-over-ranks step time, so it is the same on every rank: the exchange
+        # contains a collective)
+        probe = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ev]))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+        extra = int(min(500, max(1, 800.0 / max(float(probe), 1e-3))))
+        for k in range(extra):
+            R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
+            if k % 20 == 19:
+                torch.cuda.synchronize()
         barrier()
         # kernel-only time of the dominant kernel, measured live with CUDA events (library stats)
         for i in range(min(args.steps, 5)):
