@@ -13,8 +13,11 @@
 //   phase 3  pre-order numbering of the inner nodes = sort by (first position asc, last position desc),
 //            emission of the 64-byte traversal nodes, permutation of the primitives into DFS order
 //
-// The SurfaceAreaHeuristic split, and the degenerate case of an empty LEFT partition (only possible
-// with denormal centroids), are left to the host builder (bvh_build.cpp); gpuBuildSupported() says which.
+// SurfaceAreaHeuristic (Culling.hs:62-112): the 16 bucket counts / boxes of every segment are accumulated with
+// atomics (min / max are exact), then ONE thread per segment evaluates the reference's cost expression in the
+// reference's order (wrappedArea = left fold over the buckets, prefix / suffix joins, minimumBy with its NaN
+// behaviour) -- same floats, same split.  Segments of at most 4 primitives split at the midpoint (Culling.hs:110-112).
+// The degenerate case of an empty LEFT partition is left to the host builder (bvh_build.cpp).
 #include "bvh_build_gpu.hpp"
 
 #include <cub/cub.cuh>
@@ -39,6 +42,55 @@ __device__ __forceinline__ float centroid1(float lo, float hi) {
 // maxDimension (Vectors.hs:62-66)
 __device__ __forceinline__ int maxDim(float x, float y, float z) { return (x > y && x > z) ? 0 : (y > z ? 1 : 2); }
 __device__ __forceinline__ float comp(const float4& v, int d) { return d == 0 ? v.x : (d == 1 ? v.y : v.z); }
+
+// ---- SurfaceAreaHeuristic helpers (Culling.hs:62-112; host twin: bvh_build.cpp sahSplit) ------------------
+constexpr int kBuckets = 16;
+// bucketId = clamp (floor (16 * (c - cmin) / (cmax - cmin))); `floor x :: Int` of NaN / out of range is INT64_MIN
+__device__ __forceinline__ int bucketOf(float c, float centMin, float extent) {
+  const float frac = __fdiv_rn(__fsub_rn(c, centMin), extent);
+  const float f = floorf(__fmul_rn((float)kBuckets, frac));
+  if (!(f >= -9.2233720368547758e18f && f < 9.2233720368547758e18f)) return 0;     // INT64_MIN clamps to 0
+  if (f < 0.0f) return 0;
+  if (f > (float)(kBuckets - 1)) return kBuckets - 1;
+  return (int)f;
+}
+struct BoxD { float lo[3], hi[3]; };
+__device__ __forceinline__ BoxD emptyBoxD() {
+  BoxD b;
+  for (int c = 0; c < 3; ++c) { b.lo[c] = INFINITY; b.hi[c] = -INFINITY; }
+  return b;
+}
+// GHC class-default min / max (select semantics); inputs are never NaN here
+__device__ __forceinline__ BoxD joinD(const BoxD& a, const BoxD& b) {
+  BoxD r;
+  for (int c = 0; c < 3; ++c) { r.lo[c] = a.lo[c] <= b.lo[c] ? a.lo[c] : b.lo[c]; r.hi[c] = a.hi[c] <= b.hi[c] ? b.hi[c] : a.hi[c]; }
+  return r;
+}
+__device__ __forceinline__ float surfD(const BoxD& b) {                    // AABBs.hs:51-53
+  const float dx = __fsub_rn(b.hi[0], b.lo[0]), dy = __fsub_rn(b.hi[1], b.lo[1]), dz = __fsub_rn(b.hi[2], b.lo[2]);
+  return __fmul_rn(2.0f, __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dx, dz)), __fmul_rn(dy, dz)));
+}
+// The split bucket: primitives of buckets <= result go left.
+__device__ int sahBestSplit(const int* counts, const BoxD* boxes) {
+  float wrappedArea = 0.0f;
+  for (int b = 0; b < kBuckets; ++b) wrappedArea = __fadd_rn(wrappedArea, surfD(boxes[b]));
+  int bestSplit = 0;
+  float bestCost = 0.0f;
+  BoxD pre = emptyBoxD();
+  int cpre = 0;
+  for (int s = 0; s <= kBuckets - 2; ++s) {
+    pre = joinD(pre, boxes[s]);
+    cpre += counts[s];
+    BoxD suf = emptyBoxD();
+    int csuf = 0;
+    for (int b = s + 1; b < kBuckets; ++b) { suf = joinD(suf, boxes[b]); csuf += counts[b]; }
+    const float cost = __fadd_rn(0.125f, __fdiv_rn(__fadd_rn(__fmul_rn((float)cpre, surfD(pre)), __fmul_rn((float)csuf, surfD(suf))),
+                                                   wrappedArea));
+    // minimumBy (compare `on` snd): the accumulator is replaced unless acc < next or acc == next
+    if (s == 0 || !((bestCost < cost) || (bestCost == cost))) { bestSplit = s; bestCost = cost; }
+  }
+  return bestSplit;
+}
 
 // ---- phase 0 ------------------------------------------------------------------------------------------
 __global__ void k_prim_bounds(GpuBuildInput in, float4* blo, float4* bhi, float4* cen, uint32_t* idx, uint32_t* segOf,
@@ -89,6 +141,9 @@ struct Segs {            // active (large) segments of the current level
   uint32_t* acc;         // 12 ordered-uint accumulators per segment: cmin3 cmax3 bmin3 bmax3
   uint32_t* mode;        // 0 = became a leaf, 1 = split
   uint32_t* dim; float* mid;
+  float* cmin; float* extent;          // SAH: centroid bounds along `dim`
+  uint32_t* split;                     // SAH: split bucket, or kInvalid = midpoint rule (<= 4 primitives never happens here)
+  uint32_t* bacc;                      // SAH: per segment 16 x (count, lo3, hi3) ordered-uint accumulators
   uint32_t* leftCount; uint32_t* leftSeg; uint32_t* rightSeg;   // child segment ids (kInvalid: small / leaf)
 };
 
@@ -150,7 +205,47 @@ __global__ void k_seg_decide(Segs s, uint32_t nSeg, int depthLeft, uint32_t leve
   const float lo = d == 0 ? cminx : (d == 1 ? cminy : cminz), hi = d == 0 ? cmaxx : (d == 1 ? cmaxy : cmaxz);
   s.dim[i] = (uint32_t)d;
   s.mid[i] = centroid1(lo, hi);                                         // getDimension dim (centroid bbOfCentroids)
+  s.cmin[i] = lo;
+  s.extent[i] = __fsub_rn(hi, lo);
+  s.split[i] = kInvalid;
   s.mode[i] = 1;
+}
+
+// SAH: bucket counts and boxes of every splitting segment
+__global__ void k_bucket_init(uint32_t* bacc, uint32_t nSeg) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSeg * kBuckets * 7u) return;
+  const uint32_t k = i % 7u;
+  bacc[i] = k == 0u ? 0u : (k <= 3u ? 0xFFFFFFFFu : 0u);               // count, mins high, maxes low
+}
+
+__global__ void k_bucket_accum(uint32_t n, const uint32_t* idx, const uint32_t* segOf, const float4* blo, const float4* bhi,
+                               const float4* cen, Segs s) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t seg = segOf[i];
+  if (seg == kInvalid || !s.mode[seg]) return;
+  const uint32_t p = idx[i];
+  const int b = bucketOf(comp(cen[p], (int)s.dim[seg]), s.cmin[seg], s.extent[seg]);
+  uint32_t* a = s.bacc + ((size_t)seg * kBuckets + b) * 7u;
+  const float4 l = blo[p], h = bhi[p];
+  atomicAdd(&a[0], 1u);
+  atomicMin(&a[1], encF(l.x)); atomicMin(&a[2], encF(l.y)); atomicMin(&a[3], encF(l.z));
+  atomicMax(&a[4], encF(h.x)); atomicMax(&a[5], encF(h.y)); atomicMax(&a[6], encF(h.z));
+}
+
+__global__ void k_sah_decide(Segs s, uint32_t nSeg) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSeg || !s.mode[i]) return;
+  int counts[kBuckets];
+  BoxD boxes[kBuckets];
+  for (int b = 0; b < kBuckets; ++b) {
+    const uint32_t* a = s.bacc + ((size_t)i * kBuckets + b) * 7u;
+    counts[b] = (int)a[0];
+    if (a[0] == 0u) boxes[b] = emptyBoxD();
+    else for (int c = 0; c < 3; ++c) { boxes[b].lo[c] = decF(a[1 + c]); boxes[b].hi[c] = decF(a[4 + c]); }
+  }
+  s.split[i] = (uint32_t)sahBestSplit(counts, boxes);
 }
 
 __global__ void k_flags(uint32_t n, const uint32_t* idx, const uint32_t* segOf, const float4* cen, Segs s,
@@ -160,7 +255,11 @@ __global__ void k_flags(uint32_t n, const uint32_t* idx, const uint32_t* segOf, 
   uint32_t f = 0;
   if (i < n) {
     const uint32_t seg = segOf[i];
-    if (seg != kInvalid && s.mode[seg]) f = comp(cen[idx[i]], (int)s.dim[seg]) <= s.mid[seg] ? 1u : 0u;   // midpointSplit
+    if (seg != kInvalid && s.mode[seg]) {
+      const float c = comp(cen[idx[i]], (int)s.dim[seg]);
+      if (s.split[seg] == kInvalid) f = c <= s.mid[seg] ? 1u : 0u;                               // midpointSplit
+      else f = (uint32_t)bucketOf(c, s.cmin[seg], s.extent[seg]) <= s.split[seg] ? 1u : 0u;       // sahSplit
+    }
   }
   flags[i] = f;
 }
@@ -215,7 +314,7 @@ __global__ void k_scatter(uint32_t n, const uint32_t* idxIn, uint32_t* idxOut, c
 // One thread finishes the subtree of a segment of at most kSmall primitives (iterative buildTree).
 __global__ void k_finish_small(uint32_t nSmall, const uint32_t* smallLo, const uint32_t* smallHi, const uint32_t* smallNode,
                                uint32_t* idx, const float4* blo, const float4* bhi, const float4* cen, GpuNode* nodes,
-                               uint32_t* counters, int maxDepth) {
+                               uint32_t* counters, int maxDepth, int splitMode) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nSmall) return;
   uint32_t stLo[kSmall + 1], stHi[kSmall + 1], stNode[kSmall + 1];
@@ -246,10 +345,29 @@ __global__ void k_finish_small(uint32_t nSmall, const uint32_t* smallLo, const u
     if (maxDepth - (int)level == 0) { nd.kind = 3; continue; }                 // depth cap: multi-leaf
     const int d = maxDim(__fsub_rn(ch[0], cl[0]), __fsub_rn(ch[1], cl[1]), __fsub_rn(ch[2], cl[2]));
     const float mid = centroid1(cl[d], ch[d]);
+    int sahSplit = -1;                                                          // -1: midpoint rule
+    const float centMin = cl[d], extent = __fsub_rn(ch[d], cl[d]);
+    if (splitMode == 1 && count > 4u) {                                         // sahSplit (Culling.hs:62-112)
+      int counts[kBuckets];
+      BoxD boxes[kBuckets];
+      for (int b = 0; b < kBuckets; ++b) { counts[b] = 0; boxes[b] = emptyBoxD(); }
+      for (uint32_t k = lo; k < hi; ++k) {
+        const uint32_t p = idx[k];
+        const int b = bucketOf(comp(cen[p], d), centMin, extent);
+        const float4 l4 = blo[p], h4 = bhi[p];
+        BoxD pb;
+        pb.lo[0] = l4.x; pb.lo[1] = l4.y; pb.lo[2] = l4.z; pb.hi[0] = h4.x; pb.hi[1] = h4.y; pb.hi[2] = h4.z;
+        counts[b]++;
+        boxes[b] = joinD(boxes[b], pb);
+      }
+      sahSplit = sahBestSplit(counts, boxes);
+    }
     uint32_t l = lo, r = 0;
     for (uint32_t k = lo; k < hi; ++k) {                                        // stable partition
       const uint32_t p = idx[k];
-      if (comp(cen[p], d) <= mid) idx[l++] = p; else tmp[r++] = p;
+      const float c = comp(cen[p], d);
+      const bool left = sahSplit < 0 ? (c <= mid) : (bucketOf(c, centMin, extent) <= sahSplit);
+      if (left) idx[l++] = p; else tmp[r++] = p;
     }
     for (uint32_t k = 0; k < r; ++k) idx[l + k] = tmp[k];
     if (l == hi) { nd.kind = 3; continue; }                                    // right side empty: multi-leaf
@@ -362,7 +480,8 @@ struct BuildBuffers {
   uint32_t *idxA, *idxB, *segA, *segB, *flags, *scan, *counters;
   GpuNode* nodes;
   uint32_t *sLo[2], *sHi[2], *sNode[2], *acc, *mode, *dim, *leftCount, *leftSeg, *rightSeg, *smLo, *smHi, *smNode;
-  float* mid;
+  uint32_t *split, *bacc;
+  float *mid, *cmin, *extent;
   unsigned char *scanTemp, *sortTemp;
   unsigned long long *keysIn, *keysOut;
   uint32_t *idsIn, *idsOut, *preIdx;
@@ -373,7 +492,8 @@ struct BuildBuffers {
     nodes = a.take<GpuNode>(2 * (size_t)n);
     for (int k = 0; k < 2; ++k) { sLo[k] = a.take<uint32_t>(maxSeg); sHi[k] = a.take<uint32_t>(maxSeg); sNode[k] = a.take<uint32_t>(maxSeg); }
     acc = a.take<uint32_t>(12 * maxSeg); mode = a.take<uint32_t>(maxSeg); dim = a.take<uint32_t>(maxSeg);
-    mid = a.take<float>(maxSeg);
+    mid = a.take<float>(maxSeg); cmin = a.take<float>(maxSeg); extent = a.take<float>(maxSeg);
+    split = a.take<uint32_t>(maxSeg); bacc = a.take<uint32_t>(maxSeg * kBuckets * 7);
     leftCount = a.take<uint32_t>(maxSeg); leftSeg = a.take<uint32_t>(maxSeg); rightSeg = a.take<uint32_t>(maxSeg);
     smLo = a.take<uint32_t>(n); smHi = a.take<uint32_t>(n); smNode = a.take<uint32_t>(n);
     scanTemp = a.take<unsigned char>(scanBytes); sortTemp = a.take<unsigned char>(sortBytes);
@@ -404,9 +524,9 @@ inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + pe
 
 }  // namespace
 
-bool gpuBuildSupported(int splitMode) { return splitMode == 0; }
+bool gpuBuildSupported(int splitMode) { return splitMode == 0 || splitMode == 1; }
 
-bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, GpuBuildOutput& out) {
+bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, int splitMode, GpuBuildOutput& out) {
   out = GpuBuildOutput();
   const uint32_t n = in.nPrims;
   if (n == 0) return true;                                   // bvh _ _ [] = const Nothing
@@ -452,10 +572,16 @@ bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, GpuBuildOutput& out
   uint32_t level = 0;
   while (nSeg > 0) {
     if (level > 200) { out.tooDeep = true; break; }
-    Segs s{B.sLo[cur], B.sHi[cur], B.sNode[cur], B.acc, B.mode, B.dim, B.mid, B.leftCount, B.leftSeg, B.rightSeg};
+    Segs s{B.sLo[cur], B.sHi[cur], B.sNode[cur], B.acc,  B.mode,      B.dim,     B.mid,     B.cmin, B.extent,
+           B.split,    B.bacc,     B.leftCount,  B.leftSeg, B.rightSeg};
     k_acc_init<<<blocks(12 * (size_t)nSeg), 256, 0, st>>>(B.acc, nSeg);
     k_seg_bounds<<<blocks(n), 256, 0, st>>>(n, idxIn, segIn, B.blo, B.bhi, B.cen, B.acc);
     k_seg_decide<<<blocks(nSeg), 256, 0, st>>>(s, nSeg, maxDepth - (int)level, level, B.nodes);
+    if (splitMode == 1) {            // large segments always hold more than 4 primitives: sahSplit proper
+      k_bucket_init<<<blocks((size_t)nSeg * kBuckets * 7), 256, 0, st>>>(B.bacc, nSeg);
+      k_bucket_accum<<<blocks(n), 256, 0, st>>>(n, idxIn, segIn, B.blo, B.bhi, B.cen, s);
+      k_sah_decide<<<blocks(nSeg, 64), 64, 0, st>>>(s, nSeg);
+    }
     k_flags<<<blocks((size_t)n + 1), 256, 0, st>>>(n, idxIn, segIn, B.cen, s, B.flags);
     GB(cub::DeviceScan::ExclusiveSum(B.scanTemp, scanBytes, B.flags, B.scan, (int)(n + 1), st));
     GB(cudaMemsetAsync(B.counters + 1, 0, sizeof(uint32_t), st));
@@ -476,7 +602,7 @@ bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, GpuBuildOutput& out
   const uint32_t nSmall = hostCounters[2];
   const uint32_t lastLargeLevel = level ? level - 1 : 0;
   if (nSmall) k_finish_small<<<blocks(nSmall, 64), 64, 0, st>>>(nSmall, B.smLo, B.smHi, B.smNode, idxIn, B.blo, B.bhi, B.cen,
-                                                                B.nodes, B.counters, maxDepth);
+                                                                B.nodes, B.counters, maxDepth, splitMode);
   GB(cudaMemcpyAsync(hostCounters, B.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GB(cudaStreamSynchronize(st));
   GB(cudaGetLastError());

@@ -42,7 +42,7 @@ struct GpuBuildOutput {
 
 bool gpuBuildSupported(int splitMode);
 // Returns false on a CUDA error (out.error / out.where).  On success check errorFlags / unsupported / tooDeep.
-bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, GpuBuildOutput& out);
+bool buildBvhOnDevice(const GpuBuildInput& in, int maxDepth, int splitMode, GpuBuildOutput& out);
 void freeGpuBuildOutput(GpuBuildOutput& out);
 
 }  // namespace yb

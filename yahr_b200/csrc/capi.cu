@@ -464,7 +464,7 @@ int createSceneOnDevice(const yahr_scene_desc* d, yahr_scene** out) {
     in.primOrder = arenaCopy(d->prim_order, (size_t)n, inputArena, off);
     CU(cudaStreamSynchronize(0));
     const double t1 = nowMs();
-    if (!buildBvhOnDevice(in, d->bvh_max_depth, bo)) {
+    if (!buildBvhOnDevice(in, d->bvh_max_depth, d->split_mode, bo)) {
       cleanup(); freeGpuBuildOutput(bo);
       throw CudaFailure{bo.error, bo.where, __FILE__, __LINE__};
     }
@@ -533,8 +533,8 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
   try {
     if (yahr_b200_device_count() < 1)
       return fail(YAHR_ERR_NO_DEVICE, "no CUDA device available (libyahr_b200 has no CPU fallback)");
-    // Default: build the BVH on the device (Midpoint split).  SurfaceAreaHeuristic, the degenerate
-    // cases the device builder declines, and YAHR_B200_HOST_BUILD=1 use the host builder below.
+    // Default: build the BVH on the device (both split modes).  The degenerate cases the device builder
+    // declines, and YAHR_B200_HOST_BUILD=1, use the host builder below.
     if (desc && gpuBuildSupported(desc->split_mode) && !getenv("YAHR_B200_HOST_BUILD")) {
       int rcDev = createSceneOnDevice(desc, &sc);
       if (rcDev == YAHR_OK) { *out = sc; return YAHR_OK; }
