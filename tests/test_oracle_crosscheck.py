@@ -337,3 +337,91 @@ def test_camera_ray_agrees_bit_for_bit(L):
             assert same_bits(out[0:3], origin), (k, u, v)
             assert same_bits(out[3:6], d), (k, u, v)
             assert out[6] == np.float32(1e6)
+
+
+# ---- Rays.hs:36-54, Lights.hs:15-24, Integrators.hs:22-61 -------------------------------------------------------
+def collide_all(prims, x0, u, tmax):
+    """collideAll over the primitive list in order: every Just replaces the hit and cuts the ray (Rays.hs:39-46).
+    (The BVH returns the same hit as the plain list whenever no two hits tie exactly: Spec.hs:221-262.)"""
+    best = None
+    for k, pr in enumerate(prims):
+        if pr[0] == "sphere":
+            h = collide_sphere(pr[1], pr[2], x0, u, tmax)
+        else:
+            h = collide_triangle(*pr[1:7], x0, u, tmax)
+        if h is not None:
+            best = (k, h)
+            tmax = h[0]
+    return best
+
+
+def reflection_dir(u, n):             # u - 2 * (u .* n) @* n                                   Integrators.hs:46-47
+    return vsub(u, scale(F(2) * dot(u, n), n))
+
+
+def radiance(prims, mats, lights, depth, x0, u):
+    if depth == 0:
+        return V((0, 0, 0))
+    hit = collide_all(prims, x0, u, F(1e6))
+    if hit is None:
+        return V((0, 0, 0))
+    k, (t, x, n, dpdu, _) = hit
+    diffuse, specular, exponent = mats[prims[k][-1]]
+    wo = (-u[0], -u[1], -u[2])
+    r = reflection_dir(u, n)
+    rs = radiance(prims, mats, lights, depth - 1, vadd(x, scale(F(0.001), r)), r)
+    refl = vmul(scale(dot(n, r), bsdf_at(diffuse, specular, exponent, n, dpdu, r, wo)), rs)
+    total = V((0, 0, 0))
+    for (lpos, spectrum) in lights:
+        ptl = vsub(lpos, x)
+        ldir = norm(ptl)
+        intensity = scale(F(1) / dot(ptl, ptl), spectrum)
+        kk = bsdf_at(diffuse, specular, exponent, n, dpdu, ldir, wo)
+        contrib = V((0, 0, 0))
+        if dot(kk, kk) > 0:
+            p0 = vadd(x, scale(F(0.001), ldir))
+            d = vsub(lpos, p0)
+            if collide_all(prims, p0, norm(d), np.sqrt(dot(d, d))) is None:          # reachable
+                contrib = vmul(scale(abs(dot(ldir, n)), kk), intensity)
+        total = vadd(total, contrib)
+    return vadd(refl, total)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_integrator_agrees(depth):
+    """radiance / vhit / directIllumination / illuminationAtPoint / reachable, restated a second time, against the
+    oracle on a small random scene (spheres + triangles, two lights); differences only through powf."""
+    rng = np.random.default_rng(6)
+    ns, nt = 6, 8
+    sph_c = rng.uniform(-3, 3, (ns, 3)).astype(np.float32)
+    sph_r = rng.uniform(0.4, 1.0, ns).astype(np.float32)
+    tp = (rng.uniform(-4, 4, (nt, 1, 3)) + rng.uniform(-2.5, 2.5, (nt, 3, 3))).astype(np.float32)
+    tn = np.cross(tp[:, 1] - tp[:, 0], tp[:, 2] - tp[:, 0]).astype(np.float32)
+    toward_origin = (np.einsum("ij,ij->i", tn, -tp[:, 0]) < 0)
+    tn[toward_origin] *= -1                                  # mostly face the camera region
+    mats = np.array([[0.8, 0.6, 0.4, 0.3, 0.3, 0.3, 10], [0.2, 0.7, 0.9, 0.5, 0.5, 0.5, 40]], np.float32)
+    lights = np.array([[5, 8, -6, 80, 80, 80], [-6, 4, 5, 40, 30, 20]], np.float32)
+    sc = dict(tri_p0=tp[:, 0], tri_p1=tp[:, 1], tri_p2=tp[:, 2], tri_n0=tn, tri_n1=tn, tri_n2=tn,
+              tri_material=(np.arange(nt) % 2).astype(np.uint32), sph_center=sph_c, sph_radius=sph_r,
+              sph_material=(np.arange(ns) % 2).astype(np.uint32), prim_order=None, materials=mats, lights=lights,
+              bvh_max_depth=16, split_mode=0)
+    prims = [("sphere", F(sph_r[k]), V(sph_c[k]), k % 2) for k in range(ns)]
+    prims += [("tri", V(tp[k, 0]), V(tp[k, 1]), V(tp[k, 2]), V(tn[k]), V(tn[k]), V(tn[k]), k % 2) for k in range(nt)]
+    mm = [(V(m[0:3]), V(m[3:6]), F(m[6])) for m in mats]
+    ll = [(V(li[0:3]), V(li[3:6])) for li in lights]
+    o = ob.OracleScene(sc)
+    lit = 0
+    with np.errstate(all="ignore"):
+        for k in range(150):
+            x0 = rng.uniform(-9, 9, 3).astype(np.float32)
+            aim = rng.uniform(-2.5, 2.5, 3).astype(np.float32)
+            u = np.asarray(norm(V(aim - x0)), np.float32)
+            mine = np.asarray(radiance(prims, mm, ll, depth, V(x0), V(u)), np.float32)
+            got = o.radiance(x0, u, depth=depth)
+            assert np.array_equal(np.isnan(mine), np.isnan(got)), k
+            ok = ~np.isnan(mine)
+            assert np.array_equal(mine[ok] == 0, np.asarray(got)[ok] == 0), (k, mine, got)
+            assert np.allclose(mine[ok], np.asarray(got)[ok], rtol=2e-5, atol=1e-7), (k, mine, got)
+            lit += int((mine[ok] > 0).any())
+    o.close()
+    assert lit > 40
