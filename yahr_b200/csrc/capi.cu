@@ -101,7 +101,7 @@ struct yahr_scene {
   unsigned char* wfVis[2] = {nullptr, nullptr};
   size_t wfEntries[2] = {0, 0};
   uint32_t* wfWork = nullptr;              // 2 x 8 counters
-  float *wfSampleBuf = nullptr, *wfAccum = nullptr; size_t wfPixels = 0;
+  float *wfSampleBuf = nullptr, *wfAccum = nullptr; size_t wfPixels = 0;   // wfSampleBuf holds wfPixels per-sample pixels
   int numSMs = 148;
   // frame buffers of the host-buffer entry (grown on demand)
   float* d_rgb = nullptr;
@@ -204,6 +204,7 @@ struct FramePlan {
   WavefrontParams W{};
   bool wavefront = false;
   uint32_t entriesPerItem = 1;
+  uint32_t samplesPerLaunch = 1;      // spp > 1: samples of every pixel traced by one launch
 };
 
 int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* opts, float* d_rgb, uint32_t* d_primid,
@@ -246,11 +247,24 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     const uint32_t nL = sc->dev.nSlots;          // light slots: point lights + every area-light sample
     plan.entriesPerItem = nL > 1 ? nL : 1;
     const size_t px = (size_t)cs.width * cs.height;
-    if (opts->spp > 1 && px > sc->wfPixels) {
+    // spp > 1: one launch traces several samples of every pixel (fewer, larger launches: the persistent kernels'
+    // ramp-up and tail are paid once per launch).  As many as fit a scratch budget of ~6 GB for the shadow queue.
+    plan.samplesPerLaunch = 1;
+    if (opts->spp > 1) {
+      const double perSample = (double)ts.nItems * plan.entriesPerItem * 49.0 + (double)px * 12.0;
+      double fit = perSample > 0 ? 6.0e9 / perSample : 1.0;
+      const double idxLimit = 2.0e9 / ((double)(ts.nItems ? ts.nItems : 1) * plan.entriesPerItem);    // 32-bit entry indices
+      if (fit > idxLimit) fit = idxLimit;
+      uint32_t k = fit < 1.0 ? 1u : (fit > 16.0 ? 16u : (uint32_t)fit);
+      if (const char* env = getenv("YAHR_B200_SAMPLES_PER_LAUNCH")) k = (uint32_t)atoi(env) < 1u ? 1u : (uint32_t)atoi(env);
+      if (k > (uint32_t)opts->spp) k = (uint32_t)opts->spp;
+      plan.samplesPerLaunch = k;
+    }
+    if (opts->spp > 1 && px * plan.samplesPerLaunch > sc->wfPixels) {
       cudaFree(sc->wfSampleBuf); cudaFree(sc->wfAccum); sc->wfSampleBuf = sc->wfAccum = nullptr; sc->wfPixels = 0;
-      CU(cudaMalloc(&sc->wfSampleBuf, px * 3 * sizeof(float)));
+      CU(cudaMalloc(&sc->wfSampleBuf, px * plan.samplesPerLaunch * 3 * sizeof(float)));
       CU(cudaMalloc(&sc->wfAccum, px * 3 * sizeof(float)));
-      sc->wfPixels = px;
+      sc->wfPixels = px * plan.samplesPerLaunch;
     }
     if (!sc->wfWork) {
       CU(cudaMalloc(&sc->wfWork, 16 * sizeof(uint32_t)));
@@ -269,6 +283,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.wideTree = ((tune >> 10) & 1u) ^ 1u;         // default: 4-wide tree (bit 10 set = binary tree)
     W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
+    W.samplesPerLaunch = plan.samplesPerLaunch;
   }
   return YAHR_OK;
 }
@@ -280,7 +295,8 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
   const TileSet& ts = *plan.ts;
   if (plan.wavefront) {
     WavefrontParams W = plan.W;
-    const size_t entries = (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) * plan.entriesPerItem;
+    const size_t entries = (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) * plan.entriesPerItem *
+                           plan.samplesPerLaunch;
     if (entries > sc->wfEntries[slot]) {          // grows only on the first frame of a given size
       CU(cudaDeviceSynchronize());
       cudaFree(sc->wfQ0[slot]); cudaFree(sc->wfQ1[slot]); cudaFree(sc->wfQ2[slot]); cudaFree(sc->wfVis[slot]);

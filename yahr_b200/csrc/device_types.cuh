@@ -75,7 +75,10 @@ struct WavefrontParams {
   uint32_t nItems;            // items of this launch (a range of tiles)
   uint32_t itemBase;          // tileStart value of the first tile of this launch
   const uint32_t* itemPixels; // per item of the tile set (index item + itemBase): u | v << 16, or NULL (computed)
-  uint32_t sample;            // sample index of this pass (spp > 1 runs one pass per sample)
+  uint32_t sample;            // first sample index of this launch
+  uint32_t samplesPerLaunch;  // spp > 1: one launch traces this many samples of every pixel (work = sample-major)
+  uint32_t itemsPadded;       // nItems rounded up to a multiple of 32: work items per sample
+  uint32_t framePixels;       // width * height: pixels between the per-sample frames of sampleOut
   uint32_t dense;             // several lights: shadow slots entry = item * nLights + light
   uint32_t leafThreshold;     // leaf parking: run the leaf code once this many lanes hold a leaf
   uint32_t blocksPerSM;       // tuning: persistent CTAs per SM (0 = as many as fit)

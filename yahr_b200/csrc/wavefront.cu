@@ -349,7 +349,7 @@ __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, u
 // vhit / directIllumination (Integrators.hs:32-61) up to the point where `reachable` is needed.
 template <bool AREA>
 __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool valid, uint32_t item, uint32_t pixel,
-                                             const Ray& r, float tHit, uint32_t idx, unsigned lane) {
+                                             const Ray& r, float tHit, uint32_t idx, unsigned lane, uint32_t sLocal) {
   const DeviceScene& sc = W.base.sc;
   const bool hit = valid && idx != kNoHit;
   Surface surf;
@@ -358,13 +358,16 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
   uint32_t nanBits = 0;
   V3 wo = vneg(r.d);
   if (valid) {
-    float* out = W.sampleOut + 3 * (size_t)pixel;
+    // the frame of sample sLocal of this launch (sampleOut is the image itself when spp = 1)
+    const uint32_t outIndex = sLocal * W.framePixels + pixel;
+    float* out = W.sampleOut + 3 * (size_t)outIndex;
+    const bool firstSample = W.sample + sLocal == 0u;
     if (!hit) {
       out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;              // Nothing -> Vec3 0 0 0
-      if (W.base.primid && W.sample == 0) W.base.primid[pixel] = kNoHit;
+      if (W.base.primid && firstSample) W.base.primid[pixel] = kNoHit;
     } else {
       surf = surfaceAt(sc, idx, r, tHit);
-      if (W.base.primid && W.sample == 0) W.base.primid[pixel] = surf.primId;
+      if (W.base.primid && firstSample) W.base.primid[pixel] = surf.primId;
       mat = loadMaterial(sc, surf.material);
       fr = makeFrame(surf);
       // ((n . r) @* f r) * rs with rs = vcast 0 = 0 (Integrators.hs:26,37,41-43): +-0, or NaN when the
@@ -398,7 +401,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     }
     uint32_t e = 0;
     if (W.dense) {
-      e = item * sc.nSlots + slot;
+      e = (sLocal * W.nItems + item) * sc.nSlots + slot;
       if (valid && !emit) W.q0[e] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);     // empty slot
     } else {
       const unsigned m = __ballot_sync(kFull, emit);
@@ -413,7 +416,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     if (emit) {
       const V3 d = vnorm(dl);
       W.q0[e] = make_float4(p0.x, p0.y, p0.z, len(dl));          // probe origin, tMax = len (p1 - p0)
-      W.q1[e] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+      W.q1[e] = make_float4(d.x, d.y, d.z, __uint_as_float(sLocal * W.framePixels + pixel));
       W.q2[e] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(nanBits));
       ++nEmit;
     }
@@ -423,7 +426,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     doSlot(slot, xyz(__ldg(&sc.lights[2 * li + 0])), xyz(__ldg(&sc.lights[2 * li + 1])), false, mk(0, 0, 0));
   if (AREA) {
     ShadeCtx ctx;
-    ctx.seed = W.base.seed; ctx.pixel = pixel; ctx.sample = W.sample; ctx.level = 0;
+    ctx.seed = W.base.seed; ctx.pixel = pixel; ctx.sample = W.sample + sLocal; ctx.level = 0;
     for (uint32_t a = 0; a < sc.nAreaLights; ++a) {
       const AreaLightD l = loadAreaLight(sc, a);
       for (uint32_t j = 0; j < l.samples; ++j, ++slot) doSlot(slot, areaLightPoint(l, ctx, slot), l.flux, true, l.normal);
@@ -460,8 +463,10 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&W.work[0], 32u);
     base = __shfl_sync(kFull, base, 0);
-    if (base >= W.nItems) break;
-    const uint32_t item = base + lane;
+    if (base >= W.itemsPadded * W.samplesPerLaunch) break;
+    // work is sample-major: a batch never straddles two samples (itemsPadded is a multiple of 32)
+    const uint32_t sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+    const uint32_t item = base - sLocal * W.itemsPadded + lane;
     const bool valid = item < W.nItems;
     int u = 0, v = 0;
     Ray r;
@@ -470,14 +475,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     bool busy = false;
     if (valid) {
       itemPixel(W, item, u, v);
-      r = itemRay(W, u, v, W.sample);
+      r = itemRay(W, u, v, W.sample + sLocal);
       busy = travBegin(W.base.sc, r, 1e6f, s);
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
     if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
-    shadeAndEmit<AREA>(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane);
+    shadeAndEmit<AREA>(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane, sLocal);
   }
 }
 
@@ -486,7 +491,7 @@ template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t nEntries = W.dense ? W.nItems * W.base.sc.nSlots : W.work[2];
+  const uint32_t nEntries = W.dense ? W.nItems * W.samplesPerLaunch * W.base.sc.nSlots : W.work[2];
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&W.work[1], 32u);
@@ -515,8 +520,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
 
 // Several lights: sum the visible contributions of a pixel in light order (sum = foldl (+) 0).
 __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WavefrontParams W) {
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= W.nItems) return;
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;       // (sample of the launch, item) pair
+  if (item >= W.nItems * W.samplesPerLaunch) return;
   const uint32_t nL = W.base.sc.nSlots;
   V3 total = mk(0.0f, 0.0f, 0.0f);
   bool any = false;
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ Wave
   out[0] += total.x; out[1] += total.y; out[2] += total.z;
 }
 
-// spp > 1: acc = acc + sample (sample order), then pixel = acc / spp on the last sample.
+// spp > 1: acc = acc + sample for the samples of this launch in sample order, then pixel = acc / spp after the last.
 __global__ void __launch_bounds__(256) k_wf_accum(const __grid_constant__ WavefrontParams W) {
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= W.nItems) return;
@@ -543,9 +548,11 @@ __global__ void __launch_bounds__(256) k_wf_accum(const __grid_constant__ Wavefr
   itemPixel(W, item, u, v);
   const size_t p = 3 * (size_t)(W.base.width * v + u);
   const float n = (float)W.base.spp;
+  const bool last = (int)(W.sample + W.samplesPerLaunch) == W.base.spp;
   for (int c = 0; c < 3; ++c) {
-    const float a = (W.sample == 0 ? 0.0f : W.accum[p + c]) + W.sampleOut[p + c];
-    if ((int)W.sample == W.base.spp - 1) W.base.rgb[p + c] = __fdiv_rn(a, n);
+    float a = W.sample == 0 ? 0.0f : W.accum[p + c];
+    for (uint32_t k = 0; k < W.samplesPerLaunch; ++k) a = a + W.sampleOut[3 * (size_t)k * W.framePixels + p + c];
+    if (last) W.base.rgb[p + c] = __fdiv_rn(a, n);
     else W.accum[p + c] = a;
   }
 }
@@ -568,7 +575,7 @@ cudaError_t launchPixelTable(WavefrontParams W, uint32_t* table, cudaStream_t st
 
 __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   // ray counters for the stats: primary = items, shadow = probes emitted
-  atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems);
+  atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems * W.samplesPerLaunch);
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
   W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0;      // ready for the next launch
 }
@@ -588,10 +595,14 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
   if (W.nItems == 0) return cudaSuccess;
   const bool ordered = W.base.traversal == 1;
   const uint32_t itemBlocks = (W.nItems + 255u) / 256u;
-  for (int s = 0; s < W.base.spp; ++s) {
+  const uint32_t perLaunch = W.samplesPerLaunch ? W.samplesPerLaunch : 1u;
+  W.itemsPadded = (W.nItems + 31u) & ~31u;
+  W.framePixels = (uint32_t)(W.base.width * W.base.height);
+  for (int s = 0; s < W.base.spp; s += (int)perLaunch) {
     W.sample = (uint32_t)s;
+    W.samplesPerLaunch = (uint32_t)(W.base.spp - s) < perLaunch ? (uint32_t)(W.base.spp - s) : perLaunch;
     W.sampleOut = W.base.spp == 1 ? W.base.rgb : W.sampleBuf;
-    const bool timed = phaseEvents && s == 0;      // phase times of the first sample pass
+    const bool timed = phaseEvents && s == 0;      // phase times of the first launch
     if (timed) cudaEventRecord(phaseEvents[0], stream);
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
     // AREA: the scene has area lights (extension); kept out of the default instantiation
@@ -614,7 +625,10 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     else launchPersistent(ordered ? k_wf_shadow<true, false, 1> : k_wf_shadow<false, false, 1>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;
-    if (W.dense) { k_wf_resolve<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
+    if (W.dense) {
+      k_wf_resolve<<<(W.nItems * W.samplesPerLaunch + 255u) / 256u, 256, 0, stream>>>(W);
+      if (launches) *launches += 1;
+    }
     if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
     k_wf_count<<<1, 1, 0, stream>>>(W);
     if (launches) *launches += 1;
