@@ -148,8 +148,10 @@ int yahr_b200_device_count(void);                 /* 0 when no CUDA device is us
 const char* yahr_b200_last_error(void);           /* thread-local, never NULL */
 
 /* --- scene: replaces buildCollisionModel + cull (main.hs:41-60, 118; Culling.hs:21-112) -------- */
-/* Builds the reference's BVH on the host (same split decisions, same topology, same left-first
- * DFS primitive order), flattens it and uploads it once to the CURRENT CUDA device. */
+/* Builds the reference's BVH (same split decisions, same topology, same left-first DFS primitive order, both split
+ * modes) on the CURRENT CUDA device from the uploaded primitive arrays, collapses it into the 4-wide tree the
+ * traversal kernels walk, and keeps everything resident.  Degenerate inputs the device builder declines, and
+ * YAHR_B200_HOST_BUILD=1, take the host twin of the same algorithm. */
 int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out);
 void yahr_b200_scene_destroy(yahr_scene* scene);
 int yahr_b200_scene_info(const yahr_scene* scene, yahr_scene_info* out);

@@ -10,10 +10,13 @@
 //   k_wf_shadow  : persistent warps run any-hit walks over the compacted queue; an unoccluded probe
 //                  writes its contribution to the pixel (single light) or sets its visibility flag
 //                  (several lights; k_wf_resolve then sums a pixel's lights in light order).
-//   k_wf_accum   : spp > 1 only: acc += sample, and the final divide.
+//   k_wf_accum   : spp > 1 only (extension): one launch traces up to 16 samples of every pixel (sample-major
+//                  work items, per-sample frames); acc += sample in sample order, and the final divide.
 //
 // The walk is the reference's (left child first, box test on entry with the current tMax, later hit
-// replaces).  Rays visit ~20 inner nodes per leaf, so at any moment only a few lanes of a warp hold a
+// replaces), by default on the 4-wide collapse of the tree (wide_bvh.cu: same leaves, same order, same
+// tMax at every leaf; rays with a non-finite 1/u stay on the binary tree), with an inner phase specialised
+// per ray octant.  Rays visit ~10 wide nodes per leaf, so at any moment only a few lanes of a warp hold a
 // leaf; running the (long) primitive-test code for them every round wastes most of the warp.  Lanes
 // that reach a leaf therefore PARK until at least `leafThreshold` lanes hold one (or no lane has inner
 // work left); then the leaf code runs once for all of them.  Parking only delays a lane -- each ray
