@@ -260,6 +260,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
       if (k > (uint32_t)opts->spp) k = (uint32_t)opts->spp;
       plan.samplesPerLaunch = k;
     }
+    if ((double)ts.nItems * plan.entriesPerItem * plan.samplesPerLaunch >= 4.0e9 || (double)px * plan.samplesPerLaunch >= 4.0e9)
+      return fail(YAHR_ERR_INVALID_ARGUMENT, "resolution x light slots exceeds the 32-bit shadow-queue index space");
     if (opts->spp > 1 && px * plan.samplesPerLaunch > sc->wfPixels) {
       cudaFree(sc->wfSampleBuf); cudaFree(sc->wfAccum); sc->wfSampleBuf = sc->wfAccum = nullptr; sc->wfPixels = 0;
       CU(cudaMalloc(&sc->wfSampleBuf, px * plan.samplesPerLaunch * 3 * sizeof(float)));
