@@ -86,6 +86,9 @@ SMALL = {
     # extension (no reference counterpart): quad area lights, alone and next to point lights
     "bunny-area": lambda: scenes.c2_bunny_proxy(256, 144, nu=40, nv=20, area_samples=4),
     "c1-area-only": lambda: _area_only(scenes.c1_scene_yahrr(192, 192)),
+    # IEEE corner cases: zero-area triangles, camera inside a sphere, NaN shading frames, exact t ties, a light on a surface
+    "degenerate": lambda: scenes.degenerate_mix(),
+    "degenerate-sah": lambda: _with(scenes.degenerate_mix(96, 72), split_mode=1),
 }
 
 

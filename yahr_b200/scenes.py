@@ -377,3 +377,44 @@ CONFIGS = {
     "c5": c5_replicated_bunny,
     "adversarial": adversarial_shared_edges,
 }
+
+
+# ------------------------------------------------------------------------------------------
+# Degenerate inputs: what the reference does with them is defined by IEEE arithmetic alone
+# ------------------------------------------------------------------------------------------
+def degenerate_mix(width=160, height=120):
+    """Zero-area and sliver triangles (1 / 0 and 0 * inf in the Moller-Trumbore quotient), a camera INSIDE a large sphere
+    (second quadratic root), a small sphere whose +-z pole faces the camera (dpdu = n x (0,0,1) = 0: NaN shading frame,
+    Shapes.hs:23-26), duplicated coplanar triangles (exact t ties), zero shading normals, a light sitting exactly on a
+    surface, and a flat axis-aligned box in the BVH.  Geometry stays finite; the NaNs are produced by the arithmetic."""
+    sc = _empty_scene()
+    P = lambda *v: np.array(v, F)
+    tris = [
+        (P(-4, -1, 6), P(-2, -1, 6), P(-3, 1, 6)),          # regular, facing -z
+        (P(-4, -1, 6), P(-2, -1, 6), P(-3, 1, 6)),          # exact duplicate: the later one wins the tie
+        (P(2, 0, 5), P(2, 0, 5), P(2, 0, 5)),               # a point
+        (P(-3, 0, 5), P(-2, 0, 5), P(-1, 0, 5)),            # collinear: zero area
+        (P(-4, 2, 7), P(4, 2.0000002, 7), P(0, 2.0000001, 7)),   # sliver
+        (P(-6, -2, 0), P(6, -2, 0), P(6, -2, 14)),          # floor (flat box in y)
+        (P(-6, -2, 0), P(6, -2, 14), P(-6, -2, 14)),
+        (P(1.5, -1, 4), P(2.5, -1, 4), P(2, 0, 4)),         # zero shading normals: u . ns = 0 is never < 0
+    ]
+    n = len(tris)
+    p0 = np.stack([t[0] for t in tris]); p1 = np.stack([t[1] for t in tris]); p2 = np.stack([t[2] for t in tris])
+    nn = flat_normals(p0, p1, p2)
+    nn[np.isnan(nn)] = 0
+    nn[0] = nn[1] = P(0, 0, -1)
+    nn[5] = nn[6] = P(0, 1, 0)
+    nn[7] = 0
+    sc["tri_p0"], sc["tri_p1"], sc["tri_p2"] = p0, p1, p2
+    sc["tri_n0"] = sc["tri_n1"] = sc["tri_n2"] = nn.astype(F)
+    sc["tri_material"] = np.array([0, 1, 0, 0, 1, 2, 2, 0], np.uint32)
+    sc["sph_center"] = np.array([[0, 0, 0], [0, 0, 9], [3, 1, 8]], F)    # the camera sits inside the first one
+    sc["sph_radius"] = np.array([30, 0.5, 1.0], F)
+    sc["sph_material"] = np.array([2, 1, 0], np.uint32)
+    sc["materials"] = np.array([[0.9, 0.2, 0.2, 0.4, 0.4, 0.4, 8], [0.2, 0.9, 0.2, 0.2, 0.2, 0.2, 50],
+                                [0.7, 0.7, 0.7, 0.0, 0.0, 0.0, 1]], F)
+    sc["lights"] = np.array([[0, 4, 3, 60, 60, 60], [0, -2, 7, 20, 20, 20]], F)     # the second one lies ON the floor
+    sc["bvh_max_depth"] = 16
+    cam = _camera(width, height, 1.0, [0, 0, 1], [0, 1, 0], [0, 0, 0])
+    return sc, cam
