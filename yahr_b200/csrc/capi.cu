@@ -90,6 +90,7 @@ struct yahr_scene {
   float4* d_materials = nullptr;
   float4* d_lights = nullptr;
   float4* d_areaLights = nullptr;
+  uint32_t nTriangles = 0;                // spheres only: the (short) leaf code runs at a lower parking threshold
   unsigned long long* d_counters = nullptr;
   uint32_t* d_order = nullptr;            // primitive ID per DFS position (inspection)
   yahr_scene_info info{};
@@ -278,7 +279,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
     static const uint32_t envTune = getenv("YAHR_B200_TUNE") ? (uint32_t)strtoul(getenv("YAHR_B200_TUNE"), nullptr, 0) : 0u;
     const uint32_t tune = opts->reserved[0] ? (uint32_t)opts->reserved[0] : envTune;
-    W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : 12u;
+    // leaf parking: the triangle test is long (wait for 12 lanes), the sphere test short (6); profiles/r1k
+    W.leafThreshold = (tune & 0xFF) ? (tune & 0xFF) : (sc->nTriangles ? 12u : 6u);
     W.blocksPerSM = (tune >> 16) & 0xFF;
     W.capRegisters = ((tune >> 8) & 1u) ^ 1u;      // default: capped (bit 8 set = uncapped)
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
@@ -514,6 +516,7 @@ int createSceneOnDevice(const yahr_scene_desc* d, yahr_scene** out) {
     sc->dev.rootRef = n ? bo.rootRef : kDevRefNull;
     for (int c = 0; c < 3; ++c) { sc->dev.rootLo[c] = bo.rootBox[c]; sc->dev.rootHi[c] = bo.rootBox[3 + c]; }
     sc->info.n_primitives = (uint32_t)n; sc->info.n_nodes = bo.nInner; sc->info.n_multi_leaves = bo.nMulti;
+    sc->nTriangles = d->n_triangles;
     sc->info.depth = bo.depth; sc->info.device_bytes = bytes;
     sc->info.build_ms = t2 - t1; sc->info.upload_ms = t1 - t0;
     sc->info.built_on_device = 1;
@@ -642,6 +645,7 @@ int yahr_b200_scene_create(const yahr_scene_desc* desc, yahr_scene** out) {
     sc->dev.rootLo[0] = bvh.rootBox.lo.x; sc->dev.rootLo[1] = bvh.rootBox.lo.y; sc->dev.rootLo[2] = bvh.rootBox.lo.z;
     sc->dev.rootHi[0] = bvh.rootBox.hi.x; sc->dev.rootHi[1] = bvh.rootBox.hi.y; sc->dev.rootHi[2] = bvh.rootBox.hi.z;
     sc->info.n_primitives = (uint32_t)n;
+    sc->nTriangles = desc->n_triangles;
     sc->info.n_nodes = (uint32_t)bvh.flat.size();
     sc->info.n_multi_leaves = (uint32_t)multi.size();
     sc->info.depth = bvh.depth;
