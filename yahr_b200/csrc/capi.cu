@@ -1,5 +1,6 @@
 // capi.cu -- the C ABI of libyahr_b200.so (include/yahr_b200.h).  No CPU fallback: every compute
 // entry point needs a CUDA device and fails with YAHR_ERR_NO_DEVICE / YAHR_ERR_CUDA otherwise.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -114,13 +115,19 @@ struct yahr_scene {
   cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t renderStream[2] = {nullptr, nullptr}, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
   std::vector<cudaEvent_t> bandEvents;
+  // host-buffer entry: shadow probes per band of the previous call with the same band layout (a cost estimate that
+  // orders the bands of the next call: cheap ones first)
+  uint32_t* d_bandProbes = nullptr;
+  std::vector<uint32_t> bandProbes;
+  std::tuple<int, int, int, int, int> bandKey{0, 0, 0, 0, 0};
+  float lastHostGpuMs = 0.0f;
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_areaLights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); cudaFree(kv.second.d_itemPixels); }
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
-    cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum);
+    cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto e : phaseEv) if (e) cudaEventDestroy(e);
@@ -294,7 +301,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
 
 // Enqueues the kernels for tiles [first, first + count) of the plan's tile set.
 void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_t count, cudaStream_t stream,
-                  uint32_t* launches, cudaEvent_t* phaseEv, int slot = 0) {
+                  uint32_t* launches, cudaEvent_t* phaseEv, int slot = 0, uint32_t* bandStat = nullptr) {
   if (count == 0) return;
   const TileSet& ts = *plan.ts;
   if (plan.wavefront) {
@@ -314,6 +321,7 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
     W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot];
     W.visibility = plan.entriesPerItem > 1 ? sc->wfVis[slot] : nullptr;
     W.work = sc->wfWork + 8 * slot;
+    W.bandStat = bandStat;
     W.base.tiles = ts.d_tiles + first; W.base.nTiles = count;
     W.tileStart = ts.d_tileStart + first;
     W.itemBase = ts.hostStart[first];
@@ -873,15 +881,38 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     if (timeline)
       for (uint32_t b = 0; b < nBands; ++b) { cudaEvent_t e; CU(cudaEventCreate(&e)); copyDone.push_back(e); }
     uint32_t launches = 0;
+    // Band ORDER: a band costs its rendering on the GPU and then its copy on the copy engine (a two-stage flow
+    // shop; the copies cost the same for every band).  When the copies dominate, cheap bands -- sky, ground beyond the
+    // model -- should go first, so that their copies run under the rendering of the expensive ones (Johnson's rule).
+    // The cost estimate is the number of shadow probes each band emitted in the previous call with the same band
+    // layout; the first call goes top to bottom.  Order only: every band is rendered and copied either way.
+    if (!scene->d_bandProbes) CU(cudaMalloc(&scene->d_bandProbes, 64 * sizeof(uint32_t)));
+    if (nBands > 64) nBands = 64;
+    const auto bandKey = std::make_tuple(W_, H_, (int)nBands, shardIndex, shardCount);
+    std::vector<uint32_t> order(nBands);
+    for (uint32_t b = 0; b < nBands; ++b) order[b] = b;
+    if (plan.wavefront && scene->bandKey == bandKey && scene->bandProbes.size() == nBands && scene->lastHostGpuMs > 0.0f &&
+        nRows && !getenv("YAHR_B200_BANDS_IN_ORDER")) {
+      // Only when the copies are the bottleneck of the call (frame bytes at ~55 GB/s against the GPU time of the
+      // previous call); a render-bound call gains nothing from reordering and keeps top to bottom.
+      const double bytesPerPixel = (rgb_out ? 12.0 : 0.0) + (rgb8_out ? 3.0 : 0.0) + (primid_out ? 4.0 : 0.0);
+      const double copyMs = (double)ts.nItems * bytesPerPixel / 55.0e6;
+      if (copyMs >= scene->lastHostGpuMs * 0.9)
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return scene->bandProbes[a] < scene->bandProbes[b]; });
+    }
+    CU(cudaMemsetAsync(scene->d_bandProbes, 0, 64 * sizeof(uint32_t), rs));
     CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
     CU(cudaEventRecord(scene->ev0, rs));
     if (nBands > 1) CU(cudaStreamWaitEvent(rs1, scene->ev0, 0));     // counters are cleared before any band
     uint64_t d2h = 0;
-    for (uint32_t b = 0; b < nBands && nRows; ++b) {
+    for (uint32_t pos = 0; pos < nBands && nRows; ++pos) {
+      const uint32_t b = order[pos];
       const uint32_t r0 = (uint32_t)((uint64_t)nRows * b / nBands), r1 = (uint32_t)((uint64_t)nRows * (b + 1) / nBands);
       const uint32_t first = ts.rowFirst[r0], count = ts.rowFirst[r1] - ts.rowFirst[r0];
-      cudaStream_t bs = (b & 1u) ? rs1 : rs;
-      enqueueTiles(scene, plan, first, count, bs, &launches, (b == 0) ? scene->phaseEv : nullptr, (int)(b & 1u));
+      cudaStream_t bs = (pos & 1u) ? rs1 : rs;
+      enqueueTiles(scene, plan, first, count, bs, &launches, (pos == 0) ? scene->phaseEv : nullptr, (int)(pos & 1u),
+                   scene->d_bandProbes + b);
       // copies: one per run of pixel rows that is contiguous in the frame (the whole band when every row is owned)
       uint32_t r = r0;
       while (r < r1) {
@@ -925,12 +956,15 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       if (timeline) CU(cudaEventRecord(copyDone[b], cp));
     }
     if (nBands > 1) {                                  // join: the last band of each render stream
-      CU(cudaStreamWaitEvent(rs, scene->bandEvents[nBands - 1], 0));
-      CU(cudaStreamWaitEvent(rs, scene->bandEvents[nBands - 2], 0));
+      CU(cudaStreamWaitEvent(rs, scene->bandEvents[order[nBands - 1]], 0));
+      CU(cudaStreamWaitEvent(rs, scene->bandEvents[order[nBands - 2]], 0));
     }
     CU(cudaEventRecord(scene->ev1, rs));
     unsigned long long c[3];
     CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
+    scene->bandProbes.assign(nBands, 0u);
+    if (nBands) CU(cudaMemcpyAsync(scene->bandProbes.data(), scene->d_bandProbes, nBands * sizeof(uint32_t), cudaMemcpyDeviceToHost, rs));
+    scene->bandKey = bandKey;
     CU(cudaStreamSynchronize(rs));
     CU(cudaStreamSynchronize(cp));
     if (timeline && nRows) {
@@ -943,6 +977,10 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       }
       fprintf(stderr, "\n");
       for (auto e : copyDone) cudaEventDestroy(e);
+    }
+    {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, scene->ev0, scene->ev1) == cudaSuccess) scene->lastHostGpuMs = ms; else cudaGetLastError();
     }
     if (stats) {
       std::memset(stats, 0, sizeof(*stats));

@@ -90,6 +90,7 @@ struct WavefrontParams {
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)
   unsigned char* visibility;  // dense mode: per slot 1 = unoccluded
+  uint32_t* bandStat;         // host-buffer entry: += shadow probes of this launch (cost of the band, for scheduling) or NULL
   uint32_t* work;             // [0] primary work counter, [1] shadow work counter, [2] queue length, [3] probes
   float* sampleOut;           // where this pass writes its radiance (the frame, or sampleBuf for spp > 1)
   float* sampleBuf;           // W*H*3 scratch (spp > 1)

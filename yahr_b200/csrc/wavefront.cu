@@ -580,6 +580,7 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   // ray counters for the stats: primary = items, shadow = probes emitted
   atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems * W.samplesPerLaunch);
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
+  if (W.bandStat) *W.bandStat += W.work[3];
   W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0;      // ready for the next launch
 }
 
