@@ -144,6 +144,9 @@ typedef struct yahr_scene yahr_scene;
 
 /* --- library ---------------------------------------------------------------------------------- */
 int yahr_b200_abi_version(void);
+/* sizeof the ABI structs as the library was compiled (0 yahr_scene_desc, 1 yahr_camera, 2 yahr_render_opts, 3 yahr_stats,
+ * 4 yahr_scene_info), so that a foreign binding can check its own marshalling; -1 for an unknown index. */
+int yahr_b200_sizeof(int which);
 int yahr_b200_device_count(void);                 /* 0 when no CUDA device is usable */
 const char* yahr_b200_last_error(void);           /* thread-local, never NULL */
 

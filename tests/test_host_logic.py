@@ -131,6 +131,18 @@ def test_abi_exports_every_declared_symbol():
     assert api.lib().yahr_b200_abi_version() == 2
 
 
+def test_binding_struct_sizes_match_the_library():
+    """The ctypes mirrors in yahr_b200/api.py (and the byte offsets poked by hs/GpuRender.hs: 160-byte scene descriptor)
+    must have the sizes the C library was compiled with."""
+    L = api.lib()
+    L.yahr_b200_sizeof.restype = C.c_int
+    for which, cls in enumerate([api.SceneDesc, api.Camera, api.RenderOpts, api.Stats, api.SceneInfo]):
+        assert L.yahr_b200_sizeof(which) == C.sizeof(cls), cls.__name__
+    assert L.yahr_b200_sizeof(0) == 160
+    assert "allocaBytes 160" in open(os.path.join(ROOT, "hs", "GpuRender.hs")).read()
+    assert L.yahr_b200_sizeof(99) == -1
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     """Without a CUDA device scene_create must fail with YAHR_ERR_NO_DEVICE (no CPU fallback)."""
     import torch

@@ -547,6 +547,17 @@ extern "C" {
 
 int yahr_b200_abi_version(void) { return YAHR_B200_ABI_VERSION; }
 
+int yahr_b200_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(yahr_scene_desc);
+    case 1: return (int)sizeof(yahr_camera);
+    case 2: return (int)sizeof(yahr_render_opts);
+    case 3: return (int)sizeof(yahr_stats);
+    case 4: return (int)sizeof(yahr_scene_info);
+    default: return -1;
+  }
+}
+
 int yahr_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
