@@ -182,6 +182,12 @@ def cpu_baseline_run(sc, cam, target_seconds=15.0, threads=0, steps=1, warmup=0)
     from oracle import binding as ob
     from yahr_b200 import api
     w, h = api.image_size(cam)
+    if threads <= 0:
+        # every host core this process may use -- explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
     t0 = time.time()
     o = ob.OracleScene(sc)
     build_s = time.time() - t0
