@@ -183,11 +183,8 @@ def cpu_baseline_run(sc, cam, target_seconds=15.0, threads=0, steps=1, warmup=0)
     from yahr_b200 import api
     w, h = api.image_size(cam)
     if threads <= 0:
-        # every host core this process may use -- explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except Exception:
-            threads = os.cpu_count() or 1
+        threads = _host_cores()       # every host core this process may use (the oracle runs one std::thread per core;
+                                      # it does not depend on OMP_NUM_THREADS, which torchrun sets to 1)
     t0 = time.time()
     o = ob.OracleScene(sc)
     build_s = time.time() - t0
@@ -216,6 +213,13 @@ def cpu_baseline_run(sc, cam, target_seconds=15.0, threads=0, steps=1, warmup=0)
          "seconds_per_step": float(np.mean([x[1] for x in vals])), "bytes_per_ray_sample": bpr,
          "frames_per_s_extrapolated": v * 1e6 / (rays / last["tiles"] * n_tiles) if rays else None}
     return d, last
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):

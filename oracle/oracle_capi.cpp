@@ -10,9 +10,10 @@
 
 #include <chrono>
 #include <cstdio>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <sched.h>
 
 using namespace yo;
 
@@ -135,6 +136,13 @@ void yo_batch_window(int64_t w, int64_t h, int64_t num, int64_t count, int32_t* 
 // rgb: W*H*3 floats (row-major, RGB interleaved, row 0 = top; main.hs:98-107); primid: W*H
 // uint32 (0xFFFFFFFF = miss) or NULL; tprim: W*H floats or NULL.  Pixels of tiles not
 // rendered by this call are left untouched.  nthreads <= 0: all cores.
+static int hostThreads() {
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return n; }
+  const unsigned hc = std::thread::hardware_concurrency();
+  return hc ? (int)hc : 1;
+}
+
 int yo_render(void* h, const yo_camera* cam, int recursion_depth, int spp, uint64_t seed, float* rgb,
               uint32_t* primid, float* tprim, yo_stats* stats, int nthreads, int tile_stride,
               int tile_offset, int64_t n_batches_override) {
@@ -143,20 +151,22 @@ int yo_render(void* h, const yo_camera* cam, int recursion_depth, int spp, uint6
   Caster caster = makeCaster(c);
   const int64_t width = (int64_t)std::floor(c.imW), height = (int64_t)std::floor(c.imH);  // main.hs:122-123
   if (width <= 0 || height <= 0 || spp < 1 || tile_stride < 1) return 1;
-  int threads = 1;
-#ifdef _OPENMP
-  threads = nthreads > 0 ? nthreads : omp_get_max_threads();
-#endif
+  int threads = nthreads > 0 ? nthreads : hostThreads();
   const int64_t nBatches = n_batches_override > 0 ? n_batches_override : numBatches(1, width, height);
   Stats total;
   int tilesDone = 0;
   auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel num_threads(threads)
-  {
+  // One std::thread per host core; tiles are handed out through an atomic counter -- the analogue of renderPar's task
+  // pool (main.hs:86-96).  Plain threads rather than OpenMP: with OMP_NUM_THREADS=1 exported (torchrun does that to
+  // its workers) libgomp was seen to leave the whole loop to one thread whatever num_threads() said.
+  std::atomic<int64_t> nextTile{0};
+  std::mutex merge;
+  auto worker = [&]() {
     Stats st;
     int myTiles = 0;
-#pragma omp for schedule(dynamic, 1) nowait
-    for (int64_t b = tile_offset; b < nBatches; b += tile_stride) {
+    for (;;) {
+      const int64_t b = tile_offset + nextTile.fetch_add(1, std::memory_order_relaxed) * (int64_t)tile_stride;
+      if (b >= nBatches) break;
       Window win = batchWindow(width, height, b, nBatches);
       ++myTiles;
       for (int u = win.x0; u < win.x1; ++u)                 // [(u, v) | u <- [x0..x1-1], v <- [y0..y1-1]]
@@ -182,8 +192,15 @@ int yo_render(void* h, const yo_camera* cam, int recursion_depth, int spp, uint6
           if (tprim) tprim[pixel] = t0hit;
         }
     }
-#pragma omp critical
-    { total.add(st); tilesDone += myTiles; }
+    std::lock_guard<std::mutex> lock(merge);
+    total.add(st);
+    tilesDone += myTiles;
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int k = 1; k < threads; ++k) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
   }
   auto t1 = std::chrono::steady_clock::now();
   if (stats) {
@@ -295,12 +312,6 @@ void yo_bsdf_at(int kind, const float* params, const float* dg12, const float* i
   out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 float yo_sample_offset(uint64_t seed, uint32_t pixel, uint32_t s, uint32_t dim) { return sampleOffset(seed, pixel, s, dim); }
-int yo_max_threads(void) {
-#ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
-#endif
-}
+int yo_max_threads(void) { return hostThreads(); }
 
 }  // extern "C"
