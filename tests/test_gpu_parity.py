@@ -278,6 +278,42 @@ def test_host_buffer_shards_assemble_the_frame():
     s.close()
 
 
+def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch):
+    """Host-buffer entry: the streamed-row path (kernels publish finished tile rows, the host thread copies them while
+    the rest is traced) against the copy-engine bands and against the device-resident frame: bit-identical, for
+    pageable and pinned destinations, repeated calls (row sequence numbers) and changing image sizes."""
+    torch = torch_mod()
+    sc, _ = scenes.c2_bunny_proxy(384, 216, nu=40, nv=20)
+    s = api.Scene(sc)
+    for (w, h) in [(384, 216), (517, 389), (33, 70), (384, 216)]:
+        _, cam = scenes.c2_bunny_proxy(w, h, nu=40, nv=20)
+        dev = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+        dpid = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        s.render_device(cam, dev.data_ptr(), dpid.data_ptr())
+        ref, rpid = dev.cpu().numpy(), dpid.cpu().numpy().view(np.uint32)
+        monkeypatch.setenv("YAHR_B200_HOST_STREAM", "0")
+        b_rgb, b_pid, b_st = s.render(cam)
+        monkeypatch.delenv("YAHR_B200_HOST_STREAM")
+        monkeypatch.setenv("YAHR_B200_HOST_FUSED", "0")                        # streamed rows with the two-kernel set
+        t_rgb, t_pid, _ = s.render(cam)
+        monkeypatch.delenv("YAHR_B200_HOST_FUSED")
+        assert np.array_equal(t_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(t_pid, rpid)
+        fdev = torch.full((h, w, 3), float("nan"), dtype=torch.float32, device="cuda")     # fused kernel, device frame
+        s.render_device(cam, fdev.data_ptr(), None, tune=0x1000)
+        assert torch.equal(fdev.view(torch.int32), dev.view(torch.int32))
+        pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+        for rep in range(3):
+            rgb, pid, st = s.render(cam)                                       # pageable destination
+            assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(pid, rpid)
+            pinned.fill_(float("nan"))
+            s.render(cam, want_primid=False, out=(pinned.numpy(), None))       # pinned destination
+            assert np.array_equal(pinned.numpy().view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(b_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(b_pid, rpid)
+        assert st["launches"] < b_st["launches"] or h < 40       # one launch of the kernel set instead of one per band
+        assert st["d2h_bytes"] == b_st["d2h_bytes"] == w * h * 16
+    s.close()
+
+
 def test_full_size_c4_terrain_properties_and_sampled_oracle():
     """BASELINE config C4 (1M triangles, 3840x2160): determinism, and oracle parity on every
     64th tile of the full-size frame."""

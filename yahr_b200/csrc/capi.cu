@@ -76,6 +76,9 @@ struct TileSet {
   // (+ end) and the pixel rows [y0, y1) it covers
   std::vector<uint32_t> rowFirst;
   std::vector<int2> rowY;
+  // streamed host output: image row -> owned tile row, pixels per tile row
+  unsigned short* d_rowOfV = nullptr;
+  uint32_t* d_rowItems = nullptr;
 };
 
 }  // namespace
@@ -121,11 +124,21 @@ struct yahr_scene {
   std::vector<uint32_t> bandProbes;
   std::tuple<int, int, int, int, int> bandKey{0, 0, 0, 0, 0};
   float lastHostGpuMs = 0.0f;
+  // host-buffer entry, streamed rows: per-row counters, completion flags in mapped host memory, frame sequence number
+  uint32_t* d_rowDone = nullptr;
+  uint32_t* h_rowFlags = nullptr;
+  uint32_t* d_rowFlags = nullptr;
+  uint32_t rowCap = 0, rowSeq = 0;
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_areaLights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
-    for (auto& kv : tiles) { cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); cudaFree(kv.second.d_itemPixels); }
+    for (auto& kv : tiles) {
+      cudaFree(kv.second.d_tiles); cudaFree(kv.second.d_tileStart); cudaFree(kv.second.d_itemPixels);
+      cudaFree(kv.second.d_rowOfV); cudaFree(kv.second.d_rowItems);
+    }
+    cudaFree(d_rowDone);
+    if (h_rowFlags) cudaFreeHost(h_rowFlags);
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
     if (ev0) cudaEventDestroy(ev0);
@@ -193,6 +206,16 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, in
   uint64_t bytes = 0;
   ts.d_tiles = devUpload(host, bytes);
   ts.d_tileStart = devUpload(start, bytes);
+  if (byRows && !ts.rowY.empty() && ts.rowY.size() < 0xFFFFu) {
+    std::vector<unsigned short> rowOfV((size_t)h, (unsigned short)0xFFFF);
+    std::vector<uint32_t> rowItems(ts.rowY.size());
+    for (size_t r = 0; r < ts.rowY.size(); ++r) {
+      rowItems[r] = start[ts.rowFirst[r + 1]] - start[ts.rowFirst[r]];
+      for (int y = ts.rowY[r].x; y < ts.rowY[r].y; ++y) rowOfV[(size_t)y] = (unsigned short)r;
+    }
+    ts.d_rowOfV = devUpload(rowOfV, bytes);
+    ts.d_rowItems = devUpload(rowItems, bytes);
+  }
   if (ts.nItems && w <= 0xFFFF && h <= 0xFFFF && !getenv("YAHR_B200_NO_PIXEL_TABLE")) {
     CU(cudaMalloc(&ts.d_itemPixels, (size_t)ts.nItems * sizeof(uint32_t)));
     WavefrontParams T{};
@@ -293,6 +316,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
     W.wideTree = ((tune >> 10) & 1u) ^ 1u;         // default: 4-wide tree (bit 10 set = binary tree)
     W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
+    W.fused = (tune >> 12) & 1u;                   // bit 12 set = fused primary + shadow kernel (one light slot)
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
     W.samplesPerLaunch = plan.samplesPerLaunch;
   }
@@ -867,6 +891,122 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     // the scratch queues are shared with yahr_b200_render_device calls that may still be in flight
     // on a caller stream
     CU(cudaDeviceSynchronize());
+
+    // STREAMED ROWS (one light slot, 1 spp, float frame -- the reference's own configuration).  The whole share is ONE
+    // launch of the wavefront set; the kernels count finalised pixels per row of the tile grid and publish a completed
+    // row in mapped host memory (wavefront.cu, rowsSignal); this thread polls the flags and starts the device-to-host
+    // copy of every completed row at once, so the copy engine runs under the traversal at row granularity and the
+    // persistent kernels pay their ramp-up and tail once (bands: once per band).  If the kernels end before every flag
+    // has been seen the remaining rows are simply copied then, so the accounting can never lose a row.
+    // YAHR_B200_HOST_STREAM=0 selects the bands below.
+    {
+      const char* env = getenv("YAHR_B200_HOST_STREAM");
+      const uint32_t nRowsS = (uint32_t)ts.rowY.size();
+      if (plan.wavefront && !plan.W.dense && spp == 1 && rgb_out && !rgb8_out && nRowsS >= 2 && ts.d_rowOfV &&
+          !(env && atoi(env) == 0)) {
+        static const bool timelineS = getenv("YAHR_B200_TIMELINE") != nullptr;
+        if (nRowsS > scene->rowCap) {
+          cudaFree(scene->d_rowDone); scene->d_rowDone = nullptr;
+          if (scene->h_rowFlags) cudaFreeHost(scene->h_rowFlags);
+          scene->h_rowFlags = nullptr; scene->rowCap = 0;
+          CU(cudaMalloc(&scene->d_rowDone, nRowsS * sizeof(uint32_t)));
+          CU(cudaHostAlloc((void**)&scene->h_rowFlags, nRowsS * sizeof(uint32_t), cudaHostAllocMapped));
+          std::memset(scene->h_rowFlags, 0, nRowsS * sizeof(uint32_t));
+          CU(cudaHostGetDevicePointer((void**)&scene->d_rowFlags, scene->h_rowFlags, 0));
+          scene->rowCap = nRowsS; scene->rowSeq = 0;
+        }
+        if (++scene->rowSeq == 0u) {                                    // sequence wrapped: start over with clean flags
+          std::memset(scene->h_rowFlags, 0, scene->rowCap * sizeof(uint32_t));
+          scene->rowSeq = 1u;
+        }
+        const uint32_t seq = scene->rowSeq;
+        plan.W.rowOfV = ts.d_rowOfV; plan.W.rowItems = ts.d_rowItems; plan.W.rowDone = scene->d_rowDone;
+        plan.W.rowFlags = scene->d_rowFlags; plan.W.rowSeq = seq;
+        // rows complete in item order only when every batch is final at once: the fused kernel (with the two-kernel set
+        // every lit row completes in the shadow phase, after the whole primary trace)
+        if (const char* f = getenv("YAHR_B200_HOST_FUSED")) plan.W.fused = atoi(f) != 0 ? 1u : 0u;
+        else plan.W.fused = 1u;
+        uint32_t launches = 0;
+        CU(cudaMemsetAsync(scene->d_rowDone, 0, nRowsS * sizeof(uint32_t), rs));
+        CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
+        CU(cudaEventRecord(scene->ev0, rs));
+        enqueueTiles(scene, plan, 0, ts.n, rs, &launches, scene->phaseEv);
+        CU(cudaEventRecord(scene->ev1, rs));
+        uint64_t d2h = 0;
+        uint32_t nCopies = 0;
+        const size_t rowBytes = (size_t)W_ * 3 * sizeof(float), idBytes = (size_t)W_ * sizeof(uint32_t);
+        auto copyRows = [&](uint32_t r, uint32_t e) {
+          const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
+          CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
+                             (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+          d2h += (uint64_t)(y1 - y0) * rowBytes;
+          if (primid_out) {
+            CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
+                               (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
+            d2h += (uint64_t)(y1 - y0) * idBytes;
+          }
+          ++nCopies;
+        };
+        const volatile uint32_t* flags = scene->h_rowFlags;
+        std::vector<unsigned char> issued(nRowsS, 0);
+        uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
+        bool kernelsDone = false;
+        while (nIssued < nRowsS) {
+          bool progress = false;
+          while (lowest < nRowsS && issued[lowest]) ++lowest;
+          for (uint32_t r = lowest; r < nRowsS;) {
+            if (issued[r] || !(kernelsDone || flags[r] == seq)) { ++r; continue; }
+            uint32_t e = r + 1;
+            while (e < nRowsS && !issued[e] && (kernelsDone || flags[e] == seq) && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+            copyRows(r, e);
+            for (uint32_t k = r; k < e; ++k) issued[k] = 1;
+            nIssued += e - r;
+            if (!kernelsDone) flaggedRows += e - r;
+            progress = true;
+            r = e;
+          }
+          if (!progress && !kernelsDone && (++spins & 15u) == 0u) {
+            const cudaError_t q = cudaStreamQuery(rs);
+            if (q == cudaSuccess) kernelsDone = true;                  // everything is rendered: copy what is left
+            else if (q != cudaErrorNotReady) throw CudaFailure{q, "cudaStreamQuery(render stream)", __FILE__, __LINE__};
+          }
+        }
+        cudaEvent_t copyEnd = nullptr;
+        if (timelineS) { CU(cudaEventCreate(&copyEnd)); CU(cudaEventRecord(copyEnd, cp)); }
+        unsigned long long c[3];
+        CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
+        CU(cudaStreamSynchronize(rs));
+        CU(cudaStreamSynchronize(cp));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+        scene->lastHostGpuMs = ms;
+        if (timelineS) {
+          float tc = 0;
+          CU(cudaEventElapsedTime(&tc, scene->ev0, copyEnd));
+          cudaEventDestroy(copyEnd);
+          fprintf(stderr, "[yahr_b200 timeline] streamed rows: wall %.3f ms; render %.3f copy end %.3f; %u rows, %u flagged "
+                  "before the kernels ended, %u copies\n", nowMs() - w0, ms, tc, nRowsS, flaggedRows, nCopies);
+        }
+        if (stats) {
+          std::memset(stats, 0, sizeof(*stats));
+          stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
+          stats->gpu_ms = ms;
+          if (ts.n) {
+            for (int k = 0; k < 3; ++k) {
+              float pm = 0;
+              CU(cudaEventElapsedTime(&pm, scene->phaseEv[k], scene->phaseEv[k + 1]));
+              stats->phase_ms[k] = pm;
+            }
+          }
+          stats->launches = launches;
+          stats->tiles = ts.n;
+          stats->h2d_bytes = sizeof(WavefrontParams) * (uint64_t)launches;
+          stats->d2h_bytes = d2h;
+          stats->wall_ms = nowMs() - w0;
+        }
+        return YAHR_OK;
+      }
+    }
 
     // The rows of this call are rendered in BANDS of consecutive owned tile rows, and every finished band is copied
     // to the caller's buffer on a copy stream while later bands render, so the device-to-host transfer overlaps

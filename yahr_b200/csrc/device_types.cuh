@@ -86,6 +86,7 @@ struct WavefrontParams {
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
   uint32_t leafRun;           // wide walk: consecutive pending leaves of a lane are tested in one leaf phase
+  uint32_t fused;             // one light slot: k_wf_fused (each warp walks its own batch's shadow probes) instead of primary + shadow
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)
@@ -95,6 +96,14 @@ struct WavefrontParams {
   float* sampleOut;           // where this pass writes its radiance (the frame, or sampleBuf for spp > 1)
   float* sampleBuf;           // W*H*3 scratch (spp > 1)
   float* accum;               // W*H*3 running sum (spp > 1)
+  // Streamed host output (host-buffer entry, one light slot, 1 spp; NULL / 0 otherwise).  The kernels count the pixels
+  // they have finalised per ROW of the tile grid; whoever completes a row publishes it in mapped host memory, and the
+  // host thread inside yahr_b200_render starts that row's device-to-host copy while the rest of the frame is traced.
+  const unsigned short* rowOfV;   // image row v -> index of its tile row in the tile set
+  const uint32_t* rowItems;       // pixels per tile row
+  uint32_t* rowDone;              // finalised pixels per tile row (zeroed before the launch)
+  volatile uint32_t* rowFlags;    // mapped host memory: rowFlags[row] = rowSeq once the row is complete in device memory
+  uint32_t rowSeq;
 };
 
 }  // namespace yb

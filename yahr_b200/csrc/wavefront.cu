@@ -348,17 +348,52 @@ __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, u
   return cameraRay(W.base, fu, fv);
 }
 
+// Streamed host output: the lanes with `done` have just stored the final value of a pixel of tile row `row`.  One atomic
+// per distinct row of the warp (a batch touches one or two); the warp that completes a row publishes it to the host.
+// Release pattern: every lane fences its stores before the count; the publishing lane fences at system scope.
+__device__ __forceinline__ void rowsSignal(const WavefrontParams& W, uint32_t row, bool done, unsigned lane) {
+  __threadfence();
+  __syncwarp();
+  unsigned todo = __ballot_sync(kFull, done);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const uint32_t r = __shfl_sync(kFull, row, leader);
+    const unsigned m = __ballot_sync(kFull, done && row == r);
+    if ((int)lane == leader) {
+      const uint32_t n = (uint32_t)__popc(m);
+      const uint32_t before = atomicAdd(&W.rowDone[r], n);
+      if (before + n == W.rowItems[r]) {
+        __threadfence_system();
+        W.rowFlags[r] = W.rowSeq;
+      }
+    }
+    todo &= ~m;
+  }
+}
+
 // Shades the hit of one lane (all 32 lanes call this together) and emits its shadow probes.
 // vhit / directIllumination (Integrators.hs:32-61) up to the point where `reachable` is needed.
-template <bool AREA>
-__device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool valid, uint32_t item, uint32_t pixel,
-                                             const Ray& r, float tHit, uint32_t idx, unsigned lane, uint32_t sLocal) {
+// The shadow probe of a lane, kept in registers by the fused kernel (k_wf_fused) instead of the queue.
+struct LocalProbe {
+  V3 origin, dir, contrib;
+  float tMax;
+  uint32_t nanBits, row;
+  bool emit;
+};
+
+template <bool AREA, bool FUSED>
+__device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool valid, uint32_t item, uint32_t pixel, int v,
+                                             const Ray& r, float tHit, uint32_t idx, unsigned lane, uint32_t sLocal,
+                                             LocalProbe* local = nullptr) {
   const DeviceScene& sc = W.base.sc;
   const bool hit = valid && idx != kNoHit;
   Surface surf;
   Frame fr;
   MaterialD mat;
   uint32_t nanBits = 0;
+  // streamed host output: the pixel's tile row travels with the probe (bits 3.. of q2.w) so that the shadow kernel
+  // can count the pixel as finished without a division
+  const uint32_t row = (W.rowFlags && valid) ? (uint32_t)W.rowOfV[v] : 0u;
   V3 wo = vneg(r.d);
   if (valid) {
     // the frame of sample sLocal of this launch (sampleOut is the image itself when spp = 1)
@@ -377,9 +412,12 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       // weight is not finite.  Stored as the pixel's base value; the direct term is added to it.
       const V3 refl = vsub(r.d, vscale(2.0f * dot(r.d, surf.n), surf.n));
       const V3 w = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
-      const V3 base = vadd(vmul(w, mk(0.0f, 0.0f, 0.0f)), mk(0.0f, 0.0f, 0.0f));
-      out[0] = base.x; out[1] = base.y; out[2] = base.z;
+      const V3 base = vadd(vmul(w, mk(0.0f, 0.0f, 0.0f)), mk(0.0f, 0.0f, 0.0f));     // +0, or NaN
       nanBits = (base.x != base.x ? 1u : 0u) | (base.y != base.y ? 2u : 0u) | (base.z != base.z ? 4u : 0u);
+      // several slots: the base is stored now and k_wf_resolve adds to it.  One slot: every pixel is stored exactly
+      // ONCE -- here (below) when no probe is emitted, else by the shadow kernel -- so the frame may live in a
+      // peer GPU or in mapped host memory without any traffic beyond the frame itself.
+      if (W.dense) { out[0] = base.x; out[1] = base.y; out[2] = base.z; }
     }
   }
   // one probe per light SLOT with lensq k > 0 (point lights, then every sample of every area light -- the
@@ -402,6 +440,14 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
         contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
       }
     }
+    if (FUSED) {                                   // one slot, probe stays in registers
+      if (emit) {
+        local->origin = p0; local->dir = vnorm(dl); local->tMax = len(dl); local->contrib = contrib;
+        local->emit = true;
+        ++nEmit;
+      }
+      return;
+    }
     uint32_t e = 0;
     if (W.dense) {
       e = (sLocal * W.nItems + item) * sc.nSlots + slot;
@@ -420,7 +466,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       const V3 d = vnorm(dl);
       W.q0[e] = make_float4(p0.x, p0.y, p0.z, len(dl));          // probe origin, tMax = len (p1 - p0)
       W.q1[e] = make_float4(d.x, d.y, d.z, __uint_as_float(sLocal * W.framePixels + pixel));
-      W.q2[e] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(nanBits));
+      W.q2[e] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(nanBits | (row << 3)));
       ++nEmit;
     }
   };
@@ -435,24 +481,35 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       for (uint32_t j = 0; j < l.samples; ++j, ++slot) doSlot(slot, areaLightPoint(l, ctx, slot), l.flux, true, l.normal);
     }
   }
+  if (hit && !W.dense && nEmit == 0u) {
+    const float qnan = __uint_as_float(0x7FFFFFFFu);
+    float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
+    out[0] = (nanBits & 1u) ? qnan : 0.0f;
+    out[1] = (nanBits & 2u) ? qnan : 0.0f;
+    out[2] = (nanBits & 4u) ? qnan : 0.0f;
+  }
+  if (FUSED) { local->nanBits = nanBits; local->row = row; }
+  else if (W.rowFlags) rowsSignal(W, row, valid && nEmit == 0u, lane);     // pixels that are final without a shadow probe
   const uint32_t warpEmit = __reduce_add_sync(kFull, nEmit);    // shadow-ray count for the stats
   if (lane == 0 && warpEmit) atomicAdd(&W.work[3], warpEmit);
 }
 
-// Result of one shadow probe.  Single light: the pixel holds its base value (+-0 or NaN, written by
-// the shading step); an unoccluded probe overwrites it with base + (0 + contribution), which is the
-// contribution itself unless the base is NaN (flag bits in q2.w) -- no read-modify-write, so the
-// frame may live in a peer GPU.  Several lights: only the visibility flag is recorded.
-__device__ __forceinline__ void shadowResult(const WavefrontParams& W, uint32_t entry, bool unoccluded) {
-  if (W.visibility) { W.visibility[entry] = unoccluded ? 1 : 0; return; }
-  if (!unoccluded) return;
-  const float4 b = W.q1[entry], c = W.q2[entry];
-  const uint32_t nanBits = __float_as_uint(c.w);
+// Result of one shadow probe.  Single slot: the shading step left the pixel to this kernel, which stores it exactly
+// once: the base value (+0, or NaN: flag bits in q2.w) for an occluded probe, base + (0 + contribution) for an
+// unoccluded one -- no read-modify-write and no second store, so the frame may live in a peer GPU or in mapped
+// host memory.  Several slots: only the visibility flag is recorded.
+__device__ __forceinline__ uint32_t shadowResult(const WavefrontParams& W, uint32_t entry, bool unoccluded) {
+  if (W.visibility) { W.visibility[entry] = unoccluded ? 1 : 0; return 0u; }
+  const float4 b = W.q1[entry];
+  float4 c = make_float4(0.0f, 0.0f, 0.0f, W.q2[entry].w);
+  if (unoccluded) c = W.q2[entry];
+  const uint32_t nanBits = __float_as_uint(c.w) & 7u;
   const float qnan = __uint_as_float(0x7FFFFFFFu);
   float* out = W.sampleOut + 3 * (size_t)__float_as_uint(b.w);
   out[0] = (nanBits & 1u) ? qnan : 0.0f + c.x;
   out[1] = (nanBits & 2u) ? qnan : 0.0f + c.y;
   out[2] = (nanBits & 4u) ? qnan : 0.0f + c.z;
+  return __float_as_uint(c.w) >> 3;              // the pixel's tile row (streamed host output)
 }
 
 }  // namespace
@@ -485,7 +542,63 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     }
     if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
-    shadeAndEmit<AREA>(W, valid, item, (uint32_t)(W.base.width * v + u), r, s.tMax, s.best, lane, sLocal);
+    shadeAndEmit<AREA, false>(W, valid, item, (uint32_t)(W.base.width * v + u), v, r, s.tMax, s.best, lane, sLocal);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused variant for ONE light slot (the reference's configuration: one point light): the warp that traced and shaded
+// a batch walks the shadow probes of that batch itself, straight from registers -- no probe queue, no second kernel,
+// every pixel stored once, final, in item order.  Same arithmetic as k_wf_primary + k_wf_shadow (bit-identical
+// frames); what changes is the schedule: the probes of a batch are not compacted with those of other batches
+// (lanes without a probe idle during the any-hit walk), but pixels become final batch by batch, so the host-buffer
+// entry can stream finished tile rows to the host while the rest of the frame is traced (rowsSignal).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_constant__ WavefrontParams W) {
+  uint2 stack[64];
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[0], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= W.itemsPadded * W.samplesPerLaunch) break;
+    const uint32_t sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+    const uint32_t item = base - sLocal * W.itemsPadded + lane;
+    const bool valid = item < W.nItems;
+    int u = 0, v = 0;
+    Ray r;
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    bool busy = false;
+    if (valid) {
+      itemPixel(W, item, u, v);
+      r = itemRay(W, u, v, W.sample + sLocal);
+      busy = travBegin(W.base.sc, r, 1e6f, s);
+    } else {
+      r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    }
+    traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+    LocalProbe pr;
+    pr.emit = false; pr.nanBits = 0; pr.row = 0; pr.tMax = 0.0f;
+    pr.origin = mk(0, 0, 0); pr.dir = mk(0, 0, 1); pr.contrib = mk(0, 0, 0);
+    const uint32_t pixel = (uint32_t)(W.base.width * v + u);
+    shadeAndEmit<false, true>(W, valid, item, pixel, v, r, s.tMax, s.best, lane, sLocal, &pr);
+    if (__any_sync(kFull, pr.emit)) {
+      // reachable (Rays.hs:49-54): any-hit walk of this batch's own probes
+      r = makeRay(pr.origin, pr.dir);
+      s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+      busy = pr.emit && travBegin(W.base.sc, r, pr.tMax, s);
+      traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+      if (pr.emit) {
+        const bool unoccluded = s.best == kNoHit;
+        const float qnan = __uint_as_float(0x7FFFFFFFu);
+        float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
+        out[0] = (pr.nanBits & 1u) ? qnan : 0.0f + (unoccluded ? pr.contrib.x : 0.0f);
+        out[1] = (pr.nanBits & 2u) ? qnan : 0.0f + (unoccluded ? pr.contrib.y : 0.0f);
+        out[2] = (pr.nanBits & 4u) ? qnan : 0.0f + (unoccluded ? pr.contrib.z : 0.0f);
+      }
+    }
+    if (W.rowFlags) rowsSignal(W, pr.row, valid, lane);
   }
 }
 
@@ -517,7 +630,9 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
     }
     if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
-    if (probe) shadowResult(W, entry, s.best == kNoHit);
+    uint32_t row = 0;
+    if (probe) row = shadowResult(W, entry, s.best == kNoHit);
+    if (W.rowFlags) rowsSignal(W, row, probe, lane);
   }
 }
 
@@ -611,6 +726,16 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
     // AREA: the scene has area lights (extension); kept out of the default instantiation
     const bool area = W.base.sc.nAreaLights != 0;
+    const bool fused = wide && !area && !W.dense && W.fused;
+    if (fused) {
+      launchPersistent(k_wf_fused<8>, W, numSMs, stream);
+      if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
+      if (launches) *launches += 1;
+      if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
+      k_wf_count<<<1, 1, 0, stream>>>(W);
+      if (launches) *launches += 1;
+      continue;
+    }
     if (area)
       launchPersistent(wide ? k_wf_primary<false, 8, true, true>
                             : (ordered ? k_wf_primary<true, 8, false, true> : k_wf_primary<false, 8, false, true>),
