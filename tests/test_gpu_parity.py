@@ -294,20 +294,29 @@ def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch)
         monkeypatch.setenv("YAHR_B200_HOST_STREAM", "0")
         b_rgb, b_pid, b_st = s.render(cam)
         monkeypatch.delenv("YAHR_B200_HOST_STREAM")
-        monkeypatch.setenv("YAHR_B200_HOST_FUSED", "0")                        # streamed rows with the two-kernel set
-        t_rgb, t_pid, _ = s.render(cam)
+        monkeypatch.setenv("YAHR_B200_HOST_STREAM", "1")
+        for fused in ("0", "1", "3"):             # streamed rows with the two-kernel set / the fused kernel (both builds)
+            monkeypatch.setenv("YAHR_B200_HOST_FUSED", fused)
+            t_rgb, t_pid, _ = s.render(cam)
+            assert np.array_equal(t_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(t_pid, rpid)
         monkeypatch.delenv("YAHR_B200_HOST_FUSED")
-        assert np.array_equal(t_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(t_pid, rpid)
-        fdev = torch.full((h, w, 3), float("nan"), dtype=torch.float32, device="cuda")     # fused kernel, device frame
-        s.render_device(cam, fdev.data_ptr(), None, tune=0x1000)
-        assert torch.equal(fdev.view(torch.int32), dev.view(torch.int32))
+        monkeypatch.delenv("YAHR_B200_HOST_STREAM")
+        for tune in (0x1000, 0x3000):     # fused kernel on the device-resident frame
+            fdev = torch.full((h, w, 3), float("nan"), dtype=torch.float32, device="cuda")
+            s.render_device(cam, fdev.data_ptr(), None, tune=tune)
+            assert torch.equal(fdev.view(torch.int32), dev.view(torch.int32))
         pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+        for rep in range(6):                   # unpinned strategy: two calls with the bands, two streamed, then the faster
+            rgb, pid, _ = s.render(cam)
+            assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(pid, rpid)
+        monkeypatch.setenv("YAHR_B200_HOST_STREAM", "1")
         for rep in range(3):
             rgb, pid, st = s.render(cam)                                       # pageable destination
             assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(pid, rpid)
             pinned.fill_(float("nan"))
             s.render(cam, want_primid=False, out=(pinned.numpy(), None))       # pinned destination
             assert np.array_equal(pinned.numpy().view(np.uint32), ref.view(np.uint32))
+        monkeypatch.delenv("YAHR_B200_HOST_STREAM")
         assert np.array_equal(b_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(b_pid, rpid)
         assert st["launches"] < b_st["launches"] or h < 40       # one launch of the kernel set instead of one per band
         assert st["d2h_bytes"] == b_st["d2h_bytes"] == w * h * 16

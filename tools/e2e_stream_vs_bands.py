@@ -43,9 +43,13 @@ def main():
             pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
             frame = pinned.numpy()
         results = {}
-        for mode in ("0", "1", "1f", "0", "1", "1f"):
-            os.environ["YAHR_B200_HOST_STREAM"] = mode[0]
-            os.environ["YAHR_B200_HOST_FUSED"] = "1" if mode.endswith("f") else "0"
+        for mode in ("0", "1", "1f", "1q", "auto", "0", "1f", "auto"):
+            if mode == "auto":                                   # the entry's own measured choice
+                os.environ.pop("YAHR_B200_HOST_STREAM", None)
+                os.environ.pop("YAHR_B200_HOST_FUSED", None)
+            else:
+                os.environ["YAHR_B200_HOST_STREAM"] = mode[0]
+                os.environ["YAHR_B200_HOST_FUSED"] = {"f": "1", "q": "3"}.get(mode[-1], "0")
             frame[...] = np.nan
             ts = []
             for i in range(9):
@@ -64,12 +68,13 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             barrier()
             if rank == 0:
-                print("%-11s world %d HOST_STREAM=%s  call %.3f ms (min %.3f)  gpu_ms(rank0) %.3f launches %d" % (
+                print("%-11s world %d HOST_STREAM=%-4s  call %.3f ms (min %.3f)  gpu_ms(rank0) %.3f launches %d" % (
                     name, world, mode, float(tt.mean()), float(tt.min()), st["gpu_ms"], st["launches"]), flush=True)
                 results.setdefault(mode, frame.copy())
+            barrier()                                            # the other ranks reset the shared frame only now
         if rank == 0:
             same = True
-            for k in ("1", "1f"):
+            for k in ("1", "1f", "1q", "auto"):
                 a, b = results["0"], results[k]
                 same = same and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
             print("%-11s frames of both modes identical: %s (NaN left: %d)" % (name, same, int(np.isnan(b).sum())), flush=True)

@@ -83,6 +83,17 @@ struct TileSet {
 
 }  // namespace
 
+// Host-buffer entry: measured choice between the copy-engine bands and the streamed rows (renderHost).
+struct HostStrategy {
+  int calls = 0;
+  double msBands = 0.0, msStream = 0.0;
+  void record(bool streamed, double ms) {
+    if (calls == 1 && !streamed) msBands = ms;
+    if (calls == 3 && streamed) msStream = ms;
+    if (calls < 4) ++calls;
+  }
+};
+
 struct yahr_scene {
   int device = 0;
   DeviceScene dev{};
@@ -129,6 +140,8 @@ struct yahr_scene {
   uint32_t* h_rowFlags = nullptr;
   uint32_t* d_rowFlags = nullptr;
   uint32_t rowCap = 0, rowSeq = 0;
+  cudaEvent_t copyEv[2] = {nullptr, nullptr};
+  std::map<std::tuple<int, int, int, int, int>, HostStrategy> hostStrategy;
 
   ~yahr_scene() {
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
@@ -138,6 +151,7 @@ struct yahr_scene {
       cudaFree(kv.second.d_rowOfV); cudaFree(kv.second.d_rowItems);
     }
     cudaFree(d_rowDone);
+    for (auto e : copyEv) if (e) cudaEventDestroy(e);
     if (h_rowFlags) cudaFreeHost(h_rowFlags);
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
@@ -316,7 +330,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.packed = ((tune >> 9) & 1u) ^ 1u;            // default: packed node step (bit 9 set = generic)
     W.wideTree = ((tune >> 10) & 1u) ^ 1u;         // default: 4-wide tree (bit 10 set = binary tree)
     W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
-    W.fused = (tune >> 12) & 1u;                   // bit 12 set = fused primary + shadow kernel (one light slot)
+    W.fused = (tune >> 12) & 3u;                   // bit 12 set = fused primary + shadow kernel (one light slot); 13: 72 registers
     W.sampleOut = d_rgb; W.sampleBuf = sc->wfSampleBuf; W.accum = sc->wfAccum;
     W.samplesPerLaunch = plan.samplesPerLaunch;
   }
@@ -898,12 +912,21 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     // copy of every completed row at once, so the copy engine runs under the traversal at row granularity and the
     // persistent kernels pay their ramp-up and tail once (bands: once per band).  If the kernels end before every flag
     // has been seen the remaining rows are simply copied then, so the accounting can never lose a row.
-    // YAHR_B200_HOST_STREAM=0 selects the bands below.
+    // Which of the two wins depends on the scene (the fused kernel's any-hit walks run with the probe-emitting lanes
+    // only): the entry MEASURES it.  Per (image size, shard) the first two calls use the bands, the next two the
+    // streamed rows, and from then on the faster one (wall time of the second call of each pair; the frames are
+    // bit-identical either way).  YAHR_B200_HOST_STREAM=0 / 1 pins the bands / the streamed rows.
+    HostStrategy* strategy = nullptr;
     {
       const char* env = getenv("YAHR_B200_HOST_STREAM");
       const uint32_t nRowsS = (uint32_t)ts.rowY.size();
-      if (plan.wavefront && !plan.W.dense && spp == 1 && rgb_out && !rgb8_out && nRowsS >= 2 && ts.d_rowOfV &&
-          !(env && atoi(env) == 0)) {
+      bool useStream = plan.wavefront && !plan.W.dense && spp == 1 && rgb_out && !rgb8_out && nRowsS >= 2 && ts.d_rowOfV;
+      if (useStream && env) useStream = atoi(env) != 0;
+      else if (useStream) {
+        strategy = &scene->hostStrategy[std::make_tuple(W_, H_, shardIndex, shardCount, primid_out ? 1 : 0)];
+        useStream = strategy->calls < 2 ? false : (strategy->calls < 4 ? true : strategy->msStream < strategy->msBands);
+      }
+      if (useStream) {
         static const bool timelineS = getenv("YAHR_B200_TIMELINE") != nullptr;
         if (nRowsS > scene->rowCap) {
           cudaFree(scene->d_rowDone); scene->d_rowDone = nullptr;
@@ -924,7 +947,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         plan.W.rowFlags = scene->d_rowFlags; plan.W.rowSeq = seq;
         // rows complete in item order only when every batch is final at once: the fused kernel (with the two-kernel set
         // every lit row completes in the shadow phase, after the whole primary trace)
-        if (const char* f = getenv("YAHR_B200_HOST_FUSED")) plan.W.fused = atoi(f) != 0 ? 1u : 0u;
+        if (const char* f = getenv("YAHR_B200_HOST_FUSED")) plan.W.fused = (uint32_t)atoi(f) & 3u;
         else plan.W.fused = 1u;
         uint32_t launches = 0;
         CU(cudaMemsetAsync(scene->d_rowDone, 0, nRowsS * sizeof(uint32_t), rs));
@@ -947,21 +970,45 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
           }
           ++nCopies;
         };
+        // Copy issue policy: at most two copies in flight (one running, one queued behind it).  While the copy engine is
+        // busy the finished rows pile up and the next copy takes the whole contiguous run, so the copies grow exactly when
+        // the engine is the bottleneck (a copy costs a few microseconds of engine idle time whatever its size) and stay
+        // row-sized -- lowest latency -- when the rendering is.  The rows of a shard are not adjacent and never merge:
+        // they are queued as they complete (waiting for a free slot only added host latency to every copy).
+        for (auto& e : scene->copyEv) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const volatile uint32_t* flags = scene->h_rowFlags;
         std::vector<unsigned char> issued(nRowsS, 0);
         uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
+        int inFlight = 0, evOldest = 0, evNext = 0;
+        const uint64_t minBusyBytes = getenv("YAHR_B200_STREAM_MIN_KB") ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MIN_KB")) << 10
+                                                                         : (uint64_t)4 << 20;
         bool kernelsDone = false;
         while (nIssued < nRowsS) {
           bool progress = false;
+          while (inFlight > 0) {
+            const cudaError_t q = cudaEventQuery(scene->copyEv[evOldest]);
+            if (q == cudaErrorNotReady) break;
+            if (q != cudaSuccess) throw CudaFailure{q, "cudaEventQuery(copy)", __FILE__, __LINE__};
+            evOldest ^= 1; --inFlight;
+          }
           while (lowest < nRowsS && issued[lowest]) ++lowest;
-          for (uint32_t r = lowest; r < nRowsS;) {
+          for (uint32_t r = lowest; r < nRowsS && (kernelsDone || inFlight < 2 || shardCount > 1);) {
             if (issued[r] || !(kernelsDone || flags[r] == seq)) { ++r; continue; }
             uint32_t e = r + 1;
             while (e < nRowsS && !issued[e] && (kernelsDone || flags[e] == seq) && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+            // while the engine is busy a short run waits for its neighbours (every copy costs ~4 us of engine idle time);
+            // the rows of a shard are not adjacent and never merge
+            if (!kernelsDone && inFlight > 0 && shardCount == 1 && (uint64_t)(ts.rowY[e - 1].y - ts.rowY[r].x) * rowBytes < minBusyBytes) { r = e; continue; }
             copyRows(r, e);
+            if (!kernelsDone) {
+              if (shardCount == 1) {
+                CU(cudaEventRecord(scene->copyEv[evNext], cp));
+                evNext ^= 1; ++inFlight;
+              }
+              flaggedRows += e - r;
+            }
             for (uint32_t k = r; k < e; ++k) issued[k] = 1;
             nIssued += e - r;
-            if (!kernelsDone) flaggedRows += e - r;
             progress = true;
             r = e;
           }
@@ -1004,6 +1051,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
           stats->d2h_bytes = d2h;
           stats->wall_ms = nowMs() - w0;
         }
+        if (strategy) strategy->record(true, nowMs() - w0);
         return YAHR_OK;
       }
     }
@@ -1152,6 +1200,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       stats->d2h_bytes = d2h;
       stats->wall_ms = nowMs() - w0;
     }
+    if (strategy) strategy->record(false, nowMs() - w0);
     return YAHR_OK;
   } catch (const CudaFailure& f) {
     return cudaFail(f);

@@ -86,7 +86,8 @@ struct WavefrontParams {
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
   uint32_t leafRun;           // wide walk: consecutive pending leaves of a lane are tested in one leaf phase
-  uint32_t fused;             // one light slot: k_wf_fused (each warp walks its own batch's shadow probes) instead of primary + shadow
+  uint32_t fused;             // one light slot: k_wf_fused (each warp walks its own batch's shadow probes) instead of
+                              // primary + shadow; bit 1: the 7-CTAs-per-SM build (72 registers)
   float4* q0;                 // shadow probes: (origin.xyz, tMax)
   float4* q1;                 //                (direction.xyz, pixel index bits)
   float4* q2;                 //                (contribution.rgb, -)

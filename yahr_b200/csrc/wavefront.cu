@@ -350,9 +350,11 @@ __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, u
 
 // Streamed host output: the lanes with `done` have just stored the final value of a pixel of tile row `row`.  One atomic
 // per distinct row of the warp (a batch touches one or two); the warp that completes a row publishes it to the host.
-// Release pattern: every lane fences its stores before the count; the publishing lane fences at system scope.
+// Release pattern: the lanes' stores are ordered before the leader's RELEASE atomic by the warp barrier (cumulativity),
+// and the publishing lane fences at system scope.  The release atomic is inline PTX on purpose: __threadfence() is
+// fence.sc (MEMBAR.SC.GPU + CCTL.IVALL) and invalidates the SM's whole L1 -- once per batch that cost the walk its
+// tree hit rate (+0.3 ms per C4 frame, profiles/r1ab); atom.release.gpu is MEMBAR.ALL.GPU + ATOMG, no invalidation.
 __device__ __forceinline__ void rowsSignal(const WavefrontParams& W, uint32_t row, bool done, unsigned lane) {
-  __threadfence();
   __syncwarp();
   unsigned todo = __ballot_sync(kFull, done);
   while (todo) {
@@ -361,9 +363,10 @@ __device__ __forceinline__ void rowsSignal(const WavefrontParams& W, uint32_t ro
     const unsigned m = __ballot_sync(kFull, done && row == r);
     if ((int)lane == leader) {
       const uint32_t n = (uint32_t)__popc(m);
-      const uint32_t before = atomicAdd(&W.rowDone[r], n);
+      uint32_t before;
+      asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(before) : "l"(W.rowDone + r), "r"(n) : "memory");
       if (before + n == W.rowItems[r]) {
-        __threadfence_system();
+        __threadfence_system();                    // acquire the other warps' counts, release to the host (128 x per frame)
         W.rowFlags[r] = W.rowSeq;
       }
     }
@@ -371,8 +374,6 @@ __device__ __forceinline__ void rowsSignal(const WavefrontParams& W, uint32_t ro
   }
 }
 
-// Shades the hit of one lane (all 32 lanes call this together) and emits its shadow probes.
-// vhit / directIllumination (Integrators.hs:32-61) up to the point where `reachable` is needed.
 // The shadow probe of a lane, kept in registers by the fused kernel (k_wf_fused) instead of the queue.
 struct LocalProbe {
   V3 origin, dir, contrib;
@@ -550,9 +551,11 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
 // Fused variant for ONE light slot (the reference's configuration: one point light): the warp that traced and shaded
 // a batch walks the shadow probes of that batch itself, straight from registers -- no probe queue, no second kernel,
 // every pixel stored once, final, in item order.  Same arithmetic as k_wf_primary + k_wf_shadow (bit-identical
-// frames); what changes is the schedule: the probes of a batch are not compacted with those of other batches
-// (lanes without a probe idle during the any-hit walk), but pixels become final batch by batch, so the host-buffer
-// entry can stream finished tile rows to the host while the rest of the frame is traced (rowsSignal).
+// frames); what changes is the schedule: the probes of a batch are not compacted with those of other batches (lanes
+// without a probe idle during the any-hit walk: slower than the two-kernel set on a device-resident frame,
+// profiles/r1ab), but pixels become final batch by batch, so the host-buffer entry can stream finished tile rows to
+// the host while the rest of the frame is traced (rowsSignal).  Compacting the probes per warp first (a 64-entry ring
+// per warp, in shared memory or in global memory around L1) was measured slower still (profiles/r1ab).
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
@@ -728,7 +731,8 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool area = W.base.sc.nAreaLights != 0;
     const bool fused = wide && !area && !W.dense && W.fused;
     if (fused) {
-      launchPersistent(k_wf_fused<8>, W, numSMs, stream);
+      if (W.fused & 2u) launchPersistent(k_wf_fused<7>, W, numSMs, stream);     // experiment: 72 registers
+      else launchPersistent(k_wf_fused<8>, W, numSMs, stream);
       if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
       if (launches) *launches += 1;
       if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
