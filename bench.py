@@ -235,7 +235,7 @@ def run_reference(args):
             "cpu_baseline": {k: d[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": d["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "GHC reference cannot be built in this image (no ghc/cabal); this is the restated C++ oracle port"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     return 0
 
 
@@ -325,7 +325,9 @@ def run_ours(args):
     if world == 1:
         host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
         out = (host_rgb.numpy(), None)
-        for _ in range(max(1, args.warmup)):
+        # the host-buffer entry measures its two output strategies during its first four calls per image size (copy-engine
+        # bands / streamed rows, capi.cu renderHost) and keeps the faster one: warm up past that
+        for _ in range(max(5, args.warmup)):
             _, _, ste = R.scene.render(cam, recursion_depth=args.depth, spp=args.spp, want_primid=False, out=out)
         times = []
         for _ in range(args.steps):
@@ -360,6 +362,9 @@ def run_ours(args):
         e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(ste["h2d_bytes"]), "d2h_bytes_per_step": int(ste["d2h_bytes"]),
                "api": "yahr_b200_render (host buffers; kernel parameters up, RGB32F frame down to pinned memory)",
+               "launches_per_call": int(ste["launches"]),
+               "strategy": ("streamed rows (fused kernel, finished tile rows copied while the frame is traced)"
+                            if ste["launches"] <= 3 else "copy-engine bands") + " -- chosen by the entry's own measurement",
                "frame_d2h_copy_alone_ms": float(np.mean(tc)) * 1e3,
                "rgb8": {"value": rays_total / (rgb8_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": rgb8_ms,
                         "d2h_bytes_per_step": int(st8["d2h_bytes"]),
@@ -372,13 +377,14 @@ def run_ours(args):
         host = SharedHostFrame(w, h, rank, world, barrier=barrier)
         times = []
         ste = None
-        for i in range(args.warmup + args.steps):
+        e2e_warmup = max(5, args.warmup)               # past the entry's four strategy-measuring calls (see above)
+        for i in range(e2e_warmup + args.steps):
             flush.zero_()
             barrier()                                  # ranks leave the barrier together: a common start
             t = time.perf_counter()
             ste = R.scene.render_shard(cam, rank, world, (host.array, None), recursion_depth=args.depth, spp=args.spp)
             dt = time.perf_counter() - t               # the call returns when this rank's rows are in the host frame
-            if i >= args.warmup:
+            if i >= e2e_warmup:
                 times.append(dt)
         # a frame is complete when the slowest rank's call has returned: max over ranks, per step
         tt = torch.tensor(times, dtype=torch.float64, device="cuda")
@@ -390,6 +396,9 @@ def run_ours(args):
                "h2d_bytes_per_step": int(bytes_t[0]), "d2h_bytes_per_step": int(bytes_t[1]),
                "api": "yahr_b200_render_shard on every rank (tile rows r mod N == rank) into one shared pinned host frame"
                       + ("" if host.pinned else " (cudaHostRegister failed: pageable)"),
+               "launches_per_call": int(ste["launches"]),
+               "strategy": ("streamed rows (fused kernel, finished tile rows copied while the frame is traced)"
+                            if ste["launches"] <= 3 else "copy-engine bands") + " -- chosen by the entry's own measurement",
                "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
         host.close()
 
@@ -436,11 +445,14 @@ def run_ours(args):
                            "scene_bytes": info["device_bytes"], "bvh_build_ms": info["build_ms"]},
                 "frames_per_s": 1e3 / ms_per_step, "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     R.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
@@ -460,6 +472,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its
+    # version there) are sent to stderr; the JSON line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -193,11 +193,12 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
                                   uint32_t* d_primid_local, uint32_t* d_primid_gather, void* stream, yahr_stats* stats);
 
 /* Multi-GPU host-buffer entry.  The frame is cut into whole rows of the reference's tile grid (squareBatches,
- * Sampling.hs:5-21); this call renders rows shard_index, shard_index + shard_count, ... on the scene's GPU and
- * copies exactly those pixel rows into rgb_out / primid_out, which are FULL-frame buffers (W*H*3 floats, W*H
- * uint32), typically one pinned allocation shared by all shards.  The host runs one call per GPU concurrently (one
- * thread or process each, each with its own yahr_scene on its own device), so every GPU uses its own PCIe link and
- * no inter-GPU exchange is needed.  shard_count = 1 is yahr_b200_render. */
+ * Sampling.hs:5-21), dealt to the shards in blocks of up to four consecutive rows (block b -> shard b mod
+ * shard_count; the shards of one frame partition it for every shard_count); this call renders the blocks of
+ * shard_index on the scene's GPU and copies exactly those pixel rows into rgb_out / primid_out, which are FULL-frame
+ * buffers (W*H*3 floats, W*H uint32), typically one pinned allocation shared by all shards.  The host runs one call
+ * per GPU concurrently (one thread or process each, each with its own yahr_scene on its own device), so every GPU
+ * uses its own PCIe link and no inter-GPU exchange is needed.  shard_count = 1 is yahr_b200_render. */
 int yahr_b200_render_shard(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
                            int shard_index, int shard_count, float* rgb_out, uint32_t* primid_out, yahr_stats* stats);
 

@@ -91,9 +91,10 @@ def test_rank_rows_partition():
     api.build_library()
     for (w, h) in [(512, 512), (1920, 1080), (3840, 2160), (37, 11), (5, 300)]:
         for world in (1, 2, 3, 8):
-            owner = np.full(h, -1)
-            for r in range(world):
-                for (_, y0, y1) in tiles.rank_rows(w, h, world, r):
-                    assert (owner[y0:y1] == -1).all()
-                    owner[y0:y1] = r
-            assert (owner >= 0).all()
+            for block in (1, tiles.shard_block_rows(w, h, world), 3):
+                owner = np.full(h, -1)
+                for r in range(world):
+                    for (_, y0, y1) in tiles.rank_rows(w, h, world, r, block=block):
+                        assert (owner[y0:y1] == -1).all()
+                        owner[y0:y1] = r
+                assert (owner >= 0).all()

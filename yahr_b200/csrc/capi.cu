@@ -140,7 +140,6 @@ struct yahr_scene {
   uint32_t* h_rowFlags = nullptr;
   uint32_t* d_rowFlags = nullptr;
   uint32_t rowCap = 0, rowSeq = 0;
-  cudaEvent_t copyEv[2] = {nullptr, nullptr};
   std::map<std::tuple<int, int, int, int, int>, HostStrategy> hostStrategy;
 
   ~yahr_scene() {
@@ -151,7 +150,6 @@ struct yahr_scene {
       cudaFree(kv.second.d_rowOfV); cudaFree(kv.second.d_rowItems);
     }
     cudaFree(d_rowDone);
-    for (auto e : copyEv) if (e) cudaEventDestroy(e);
     if (h_rowFlags) cudaFreeHost(h_rowFlags);
     for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
@@ -196,8 +194,14 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, in
       }
     }
   } else {
-    // tile `num` sits in row num `quot` nx of the grid (Sampling.hs:16); rows offset, offset + stride, ...
-    for (int64_t j = offset; j < gny; j += stride) {
+    // tile `num` sits in row num `quot` nx of the grid (Sampling.hs:16).  byRows = 1: rows offset, offset + stride, ...
+    // byRows = 2 (host-buffer shards): the rows are dealt in BLOCKS of up to four consecutive rows (block b -> shard
+    // b mod stride), so that a shard's device-to-host copies are few and large (every copy costs ~5 us of copy-engine
+    // idle time) while every shard still gets at least eight blocks spread over the image.
+    int64_t block = 1;
+    if (byRows == 2) { block = gny / (8 * (int64_t)stride); block = block < 1 ? 1 : (block > 4 ? 4 : block); }
+    for (int64_t j = 0; j < gny; ++j) {
+      if ((j / block) % stride != offset) continue;
       const uint32_t firstOfRow = (uint32_t)host.size();
       int y0 = 0, y1 = 0;
       for (int64_t i = 0; i < gnx; ++i) {
@@ -272,7 +276,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
 
   // reserved[1] = 1: tile_stride / tile_offset count whole ROWS of the tile grid (host-buffer shards)
-  const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset, opts->reserved[1] == 1 ? 1 : 0);
+  const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset,
+                               (opts->reserved[1] == 1 || opts->reserved[1] == 2) ? opts->reserved[1] : 0);
   plan.ts = &ts;
   RenderParams& P = plan.P;
   P.sc = sc->dev;
@@ -872,9 +877,10 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     o.recursion_depth = recursion_depth; o.spp = spp; o.seed = seed;
     if (shardCount < 1 || shardIndex < 0 || shardIndex >= shardCount)
       return fail(YAHR_ERR_INVALID_ARGUMENT, "shard_index / shard_count invalid");
-    // the frame is cut into whole rows of the reference's tile grid; this call renders rows shardIndex,
-    // shardIndex + shardCount, ... (all of them for the single-GPU entry)
-    o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = shardCount; o.tile_offset = shardIndex; o.reserved[1] = 1;
+    // the frame is cut into whole rows of the reference's tile grid, dealt to the shards in blocks of up to four
+    // consecutive rows (tilesFor, byRows = 2); this call renders the blocks shardIndex, shardIndex + shardCount, ...
+    // (every row for the single-GPU entry)
+    o.traversal = YAHR_TRAVERSAL_REFERENCE; o.tile_stride = shardCount; o.tile_offset = shardIndex; o.reserved[1] = 2;
     {
       CameraSetup cs;
       std::string err;
@@ -970,43 +976,33 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
           }
           ++nCopies;
         };
-        // Copy issue policy: at most two copies in flight (one running, one queued behind it).  While the copy engine is
-        // busy the finished rows pile up and the next copy takes the whole contiguous run, so the copies grow exactly when
-        // the engine is the bottleneck (a copy costs a few microseconds of engine idle time whatever its size) and stay
-        // row-sized -- lowest latency -- when the rendering is.  The rows of a shard are not adjacent and never merge:
-        // they are queued as they complete (waiting for a free slot only added host latency to every copy).
-        for (auto& e : scene->copyEv) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // Copy issue policy.  Every copy costs ~5 us of copy-engine idle time whatever its size, so while the engine
+        // has work queued a short run of finished rows waits for its neighbours (rows finish roughly in order) and
+        // the copies grow exactly when the engine is the bottleneck; when it is about to run dry, whatever is ready
+        // goes out at once.  The engine's backlog is MODELLED (bytes queued at 55 GB/s), not queried: events between
+        // the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
         const volatile uint32_t* flags = scene->h_rowFlags;
         std::vector<unsigned char> issued(nRowsS, 0);
         uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
-        int inFlight = 0, evOldest = 0, evNext = 0;
-        const uint64_t minBusyBytes = getenv("YAHR_B200_STREAM_MIN_KB") ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MIN_KB")) << 10
-                                                                         : (uint64_t)4 << 20;
+        // a run that has grown to this size goes out even when the engine has work (default: no limit)
+        const uint64_t maxHeldBytes = getenv("YAHR_B200_STREAM_MAX_HELD_KB")
+                                          ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MAX_HELD_KB")) << 10 : ~(uint64_t)0;
+        double busyUntil = 0.0;                                         // ms on the nowMs() clock
         bool kernelsDone = false;
         while (nIssued < nRowsS) {
           bool progress = false;
-          while (inFlight > 0) {
-            const cudaError_t q = cudaEventQuery(scene->copyEv[evOldest]);
-            if (q == cudaErrorNotReady) break;
-            if (q != cudaSuccess) throw CudaFailure{q, "cudaEventQuery(copy)", __FILE__, __LINE__};
-            evOldest ^= 1; --inFlight;
-          }
           while (lowest < nRowsS && issued[lowest]) ++lowest;
-          for (uint32_t r = lowest; r < nRowsS && (kernelsDone || inFlight < 2 || shardCount > 1);) {
+          for (uint32_t r = lowest; r < nRowsS;) {
             if (issued[r] || !(kernelsDone || flags[r] == seq)) { ++r; continue; }
             uint32_t e = r + 1;
             while (e < nRowsS && !issued[e] && (kernelsDone || flags[e] == seq) && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
-            // while the engine is busy a short run waits for its neighbours (every copy costs ~4 us of engine idle time);
-            // the rows of a shard are not adjacent and never merge
-            if (!kernelsDone && inFlight > 0 && shardCount == 1 && (uint64_t)(ts.rowY[e - 1].y - ts.rowY[r].x) * rowBytes < minBusyBytes) { r = e; continue; }
+            const uint64_t bytes = (uint64_t)(ts.rowY[e - 1].y - ts.rowY[r].x) * rowBytes;
+            const bool canGrow = e < nRowsS && !issued[e] && ts.rowY[e].x == ts.rowY[e - 1].y;     // row e is not finished yet
+            const double now = nowMs();
+            if (!kernelsDone && canGrow && bytes < maxHeldBytes && busyUntil - now > 0.05) { r = e; continue; }
             copyRows(r, e);
-            if (!kernelsDone) {
-              if (shardCount == 1) {
-                CU(cudaEventRecord(scene->copyEv[evNext], cp));
-                evNext ^= 1; ++inFlight;
-              }
-              flaggedRows += e - r;
-            }
+            busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 55.0e6 + 0.005;
+            if (!kernelsDone) flaggedRows += e - r;
             for (uint32_t k = r; k < e; ++k) issued[k] = 1;
             nIssued += e - r;
             progress = true;

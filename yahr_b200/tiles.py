@@ -36,13 +36,23 @@ def tile_grid(width, height, num_threads=1):
     return nx, ny
 
 
-def rank_rows(width, height, world_size, rank):
-    """Row sharding (the "rows" exchange and yahr_b200_render_shard): the tile rows rank `rank` renders and the
-    pixel rows [y0, y1) each covers.  Tile row r -> rank r mod G."""
+def shard_block_rows(width, height, world_size):
+    """Rows per block of the host-buffer shards (yahr_b200_render_shard; capi.cu tilesFor, byRows = 2): up to four
+    consecutive tile rows, at least eight blocks per shard."""
+    _, ny = tile_grid(width, height)
+    return max(1, min(4, ny // (8 * world_size)))
+
+
+def rank_rows(width, height, world_size, rank, block=1):
+    """Row sharding: the tile rows rank `rank` renders and the pixel rows [y0, y1) each covers.  The rows are dealt in
+    blocks of `block` consecutive rows, block b -> rank b mod G: block = 1 for the "rows" exchange
+    (yahr_b200_render_device_shard), shard_block_rows() for the host-buffer shards (yahr_b200_render_shard)."""
     nx, ny = tile_grid(width, height)
     n = nx * ny
     out = []
-    for r in range(rank, ny, world_size):
+    for r in range(ny):
+        if (r // block) % world_size != rank:
+            continue
         ys = [api.batch_window(width, height, r * nx + i, n) for i in range(nx)]
         ys = [(y0, y1) for (x0, y0, x1, y1) in ys if x1 > x0 and y1 > y0]
         if ys:
