@@ -979,14 +979,14 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         // Copy issue policy.  Every copy costs ~5 us of copy-engine idle time whatever its size, so while the engine
         // has work queued a short run of finished rows waits for its neighbours (rows finish roughly in order) and
         // the copies grow exactly when the engine is the bottleneck; when it is about to run dry, whatever is ready
-        // goes out at once.  The engine's backlog is MODELLED (bytes queued at 55 GB/s), not queried: events between
+        // goes out at once.  The engine's backlog is MODELLED (bytes queued at 48 GB/s + 8 us per copy), not queried: events between
         // the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
         const volatile uint32_t* flags = scene->h_rowFlags;
         std::vector<unsigned char> issued(nRowsS, 0);
         uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
-        // a run that has grown to this size goes out even when the engine has work (default: no limit)
+        // a run that has grown to this size goes out even when the engine has work
         const uint64_t maxHeldBytes = getenv("YAHR_B200_STREAM_MAX_HELD_KB")
-                                          ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MAX_HELD_KB")) << 10 : ~(uint64_t)0;
+                                          ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MAX_HELD_KB")) << 10 : (uint64_t)6 << 20;
         double busyUntil = 0.0;                                         // ms on the nowMs() clock
         bool kernelsDone = false;
         while (nIssued < nRowsS) {
@@ -1001,7 +1001,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
             const double now = nowMs();
             if (!kernelsDone && canGrow && bytes < maxHeldBytes && busyUntil - now > 0.05) { r = e; continue; }
             copyRows(r, e);
-            busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 55.0e6 + 0.005;
+            busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 48.0e6 + 0.008;    // measured under load
             if (!kernelsDone) flaggedRows += e - r;
             for (uint32_t k = r; k < e; ++k) issued[k] = 1;
             nIssued += e - r;

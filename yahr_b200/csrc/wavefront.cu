@@ -133,8 +133,9 @@ __device__ __forceinline__ bool innerStep(const DeviceScene& sc, const Ray& r, c
 }
 
 // One leaf visit (collideAll over the leaf's primitives in order).  Returns false when finished.
+// anyRt: any-hit decided at run time (k_wf_fused shares ONE copy of the walk between its closest-hit and any-hit phases).
 template <bool ANY_HIT, bool ORDERED>
-__device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack) {
+__device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool anyRt = false) {
   uint32_t first, count;
   if ((s.cur & kDevRefMultiBits) == kDevRefMultiBits) {
     const uint2 ml = __ldg(&sc.multiLeaves[s.cur & 0x3FFFFFFFu]);
@@ -148,7 +149,7 @@ __device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Tr
     if (hitPrimitive(sc, idx, r, s.tMax, t)) {
       if (!ORDERED || t < s.tMax || s.best == kNoHit || idx > s.best) {
         s.best = idx; s.tMax = t;
-        if (ANY_HIT) return false;
+        if (ANY_HIT || anyRt) return false;
       }
     }
   }
@@ -158,7 +159,7 @@ __device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Tr
 // Runs the walks of a whole warp to completion with leaf parking.  `busy` per lane.
 template <bool ANY_HIT, bool ORDERED, int OCT>
 __device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
-                                             int leafThreshold) {
+                                             int leafThreshold, bool anyRt = false) {
   const RayPack rp = packRay(r);
   for (;;) {
     const bool atLeaf = busy && (s.cur & kDevRefLeafBit);
@@ -167,7 +168,7 @@ __device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray
     const unsigned mInner = __ballot_sync(kFull, atInner);
     if ((mLeaf | mInner) == 0) break;
     if (mInner == 0 || __popc(mLeaf) >= leafThreshold) {
-      if (atLeaf) busy = leafStep<ANY_HIT, ORDERED>(sc, r, s, stack);
+      if (atLeaf) busy = leafStep<ANY_HIT, ORDERED>(sc, r, s, stack, anyRt);
     }
     if (atInner) busy = innerStep<ORDERED, OCT>(sc, r, rp, s, stack);
   }
@@ -277,7 +278,7 @@ __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& 
 
 template <bool ANY_HIT>
 __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
-                                                 int leafThreshold, bool leafRun) {
+                                                 int leafThreshold, bool leafRun, bool anyRt = false) {
   const bool nanLane = busy && r.exactNaN;
   bool run = busy && !r.exactNaN;
   const unsigned mRun = __ballot_sync(kFull, run);
@@ -304,11 +305,11 @@ __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ra
       if (!__any_sync(kFull, atLeaf)) break;
       // a lane whose next pending subtree is again a leaf (siblings in one wide node) tests it right away
       if (atLeaf) {
-        do { run = leafStep<ANY_HIT, false>(sc, r, s, stack); } while (leafRun && run && (s.cur & kDevRefLeafBit));
+        do { run = leafStep<ANY_HIT, false>(sc, r, s, stack, anyRt); } while (leafRun && run && (s.cur & kDevRefLeafBit));
       }
     }
   }
-  if (__any_sync(kFull, nanLane)) traverseWarpOct<ANY_HIT, false, -1>(sc, r, s, stack, nanLane, 1);
+  if (__any_sync(kFull, nanLane)) traverseWarpOct<ANY_HIT, false, -1>(sc, r, s, stack, nanLane, 1, anyRt);
 }
 
 // item index (tile-major) -> tile.  Tiles are almost uniform in size, so a proportional guess is
@@ -580,19 +581,24 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_const
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
-    traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+    // Both walks of a batch -- closest hit, then the any-hit walk of its probes (reachable, Rays.hs:49-54) -- go through
+    // ONE copy of the traversal code (any-hit is a run-time flag of the leaf step; the loop below is not unrolled): with
+    // two inlined copies the kernel was 6400 SASS instructions and instruction fetch was its top stall (ncu:
+    // stalled_no_instruction 5.1 per issue against 1.1 in k_wf_primary, profiles/r1ac).
     LocalProbe pr;
     pr.emit = false; pr.nanBits = 0; pr.row = 0; pr.tMax = 0.0f;
     pr.origin = mk(0, 0, 0); pr.dir = mk(0, 0, 1); pr.contrib = mk(0, 0, 0);
     const uint32_t pixel = (uint32_t)(W.base.width * v + u);
-    shadeAndEmit<false, true>(W, valid, item, pixel, v, r, s.tMax, s.best, lane, sLocal, &pr);
-    if (__any_sync(kFull, pr.emit)) {
-      // reachable (Rays.hs:49-54): any-hit walk of this batch's own probes
-      r = makeRay(pr.origin, pr.dir);
-      s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
-      busy = pr.emit && travBegin(W.base.sc, r, pr.tMax, s);
-      traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
-      if (pr.emit) {
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, phase == 1);
+      if (phase == 0) {
+        shadeAndEmit<false, true>(W, valid, item, pixel, v, r, s.tMax, s.best, lane, sLocal, &pr);
+        if (!__any_sync(kFull, pr.emit)) break;
+        r = makeRay(pr.origin, pr.dir);
+        s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+        busy = pr.emit && travBegin(W.base.sc, r, pr.tMax, s);
+      } else if (pr.emit) {
         const bool unoccluded = s.best == kNoHit;
         const float qnan = __uint_as_float(0x7FFFFFFFu);
         float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
