@@ -257,12 +257,15 @@ def test_tile_sharding_partitions_the_image():
     s.close()
 
 
-def test_host_buffer_shards_assemble_the_frame():
-    """yahr_b200_render_shard: the row shards of G GPUs written into one host frame equal the single call."""
+@pytest.mark.parametrize("stream", ["0", "1"])
+def test_host_buffer_shards_assemble_the_frame(stream, monkeypatch):
+    """yahr_b200_render_shard: the row shards of G GPUs written into one host frame equal the single call, with the
+    copy-engine bands and with the streamed rows."""
     sc, cam = scenes.c2_bunny_proxy(384, 216, nu=40, nv=20)
     w, h = api.image_size(cam)
     s = api.Scene(sc)
     full, fpid, fst = s.render(cam)
+    monkeypatch.setenv("YAHR_B200_HOST_STREAM", stream)
     for G in (1, 2, 3, 8, 64):
         rgb = np.full((h, w, 3), np.nan, np.float32)
         pid = np.full((h, w), 0xABCDEF01, np.uint32)

@@ -867,6 +867,134 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
   }
 }
 
+// Host-buffer entry, STREAMED ROWS (one light slot, 1 spp, float frame -- the reference's own configuration).  The
+// whole share is ONE launch of k_wf_fused; the kernel counts finalised pixels per row of the tile grid and publishes a
+// completed row in mapped host memory (wavefront.cu, rowsSignal); this thread polls the flags and starts the
+// device-to-host copy of every completed run of rows at once, so the copy engine runs under the traversal at row
+// granularity and the persistent kernel pays its ramp-up and tail once (bands: once per band).  If the kernel ends
+// before every flag has been seen the remaining rows are simply copied then: the accounting can never lose a row.
+static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_out, uint32_t* primid_out, yahr_stats* stats,
+                               int shardCount, double w0) {
+  const TileSet& ts = *plan.ts;
+  const uint32_t nRowsS = (uint32_t)ts.rowY.size();
+  const int W_ = plan.cs.width;
+  cudaStream_t rs = scene->renderStream[0], cp = scene->copyStream;
+  static const bool timelineS = getenv("YAHR_B200_TIMELINE") != nullptr;
+  if (nRowsS > scene->rowCap) {
+    cudaFree(scene->d_rowDone); scene->d_rowDone = nullptr;
+    if (scene->h_rowFlags) cudaFreeHost(scene->h_rowFlags);
+    scene->h_rowFlags = nullptr; scene->rowCap = 0;
+    CU(cudaMalloc(&scene->d_rowDone, nRowsS * sizeof(uint32_t)));
+    CU(cudaHostAlloc((void**)&scene->h_rowFlags, nRowsS * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(scene->h_rowFlags, 0, nRowsS * sizeof(uint32_t));
+    CU(cudaHostGetDevicePointer((void**)&scene->d_rowFlags, scene->h_rowFlags, 0));
+    scene->rowCap = nRowsS; scene->rowSeq = 0;
+  }
+  if (++scene->rowSeq == 0u) {                                    // sequence wrapped: start over with clean flags
+    std::memset(scene->h_rowFlags, 0, scene->rowCap * sizeof(uint32_t));
+    scene->rowSeq = 1u;
+  }
+  const uint32_t seq = scene->rowSeq;
+  plan.W.rowOfV = ts.d_rowOfV; plan.W.rowItems = ts.d_rowItems; plan.W.rowDone = scene->d_rowDone;
+  plan.W.rowFlags = scene->d_rowFlags; plan.W.rowSeq = seq;
+  // rows complete in item order only when every batch is final at once: the fused kernel (with the two-kernel set
+  // every lit row completes in the shadow phase, after the whole primary trace)
+  if (const char* f = getenv("YAHR_B200_HOST_FUSED")) plan.W.fused = (uint32_t)atoi(f) & 3u;
+  else plan.W.fused = 1u;
+  uint32_t launches = 0;
+  CU(cudaMemsetAsync(scene->d_rowDone, 0, nRowsS * sizeof(uint32_t), rs));
+  CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
+  CU(cudaEventRecord(scene->ev0, rs));
+  enqueueTiles(scene, plan, 0, ts.n, rs, &launches, scene->phaseEv);
+  CU(cudaEventRecord(scene->ev1, rs));
+  uint64_t d2h = 0;
+  uint32_t nCopies = 0;
+  const size_t rowBytes = (size_t)W_ * 3 * sizeof(float), idBytes = (size_t)W_ * sizeof(uint32_t);
+  auto copyRows = [&](uint32_t r, uint32_t e) {
+    const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
+    CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
+                       (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+    d2h += (uint64_t)(y1 - y0) * rowBytes;
+    if (primid_out) {
+      CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
+                         (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
+      d2h += (uint64_t)(y1 - y0) * idBytes;
+    }
+    ++nCopies;
+  };
+  // Copy issue policy.  Every copy costs ~5 us of copy-engine idle time whatever its size, so while the engine
+  // has work queued a short run of finished rows waits for its neighbours (rows finish roughly in order) and
+  // the copies grow exactly when the engine is the bottleneck; when it is about to run dry, whatever is ready
+  // goes out at once.  The engine's backlog is MODELLED (bytes queued at 48 GB/s + 8 us per copy), not queried: events between
+  // the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
+  const volatile uint32_t* flags = scene->h_rowFlags;
+  std::vector<unsigned char> issued(nRowsS, 0);
+  uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
+  // a run that has grown to this size goes out even when the engine has work
+  const uint64_t maxHeldBytes = getenv("YAHR_B200_STREAM_MAX_HELD_KB")
+                                    ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MAX_HELD_KB")) << 10 : (uint64_t)6 << 20;
+  double busyUntil = 0.0;                                         // ms on the nowMs() clock
+  bool kernelsDone = false;
+  while (nIssued < nRowsS) {
+    bool progress = false;
+    while (lowest < nRowsS && issued[lowest]) ++lowest;
+    for (uint32_t r = lowest; r < nRowsS;) {
+      if (issued[r] || !(kernelsDone || flags[r] == seq)) { ++r; continue; }
+      uint32_t e = r + 1;
+      while (e < nRowsS && !issued[e] && (kernelsDone || flags[e] == seq) && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
+      const uint64_t bytes = (uint64_t)(ts.rowY[e - 1].y - ts.rowY[r].x) * rowBytes;
+      const bool canGrow = e < nRowsS && !issued[e] && ts.rowY[e].x == ts.rowY[e - 1].y;     // row e is not finished yet
+      const double now = nowMs();
+      if (!kernelsDone && canGrow && bytes < maxHeldBytes && busyUntil - now > 0.05) { r = e; continue; }
+      copyRows(r, e);
+      busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 48.0e6 + 0.008;    // measured under load
+      if (!kernelsDone) flaggedRows += e - r;
+      for (uint32_t k = r; k < e; ++k) issued[k] = 1;
+      nIssued += e - r;
+      progress = true;
+      r = e;
+    }
+    if (!progress && !kernelsDone && (++spins & 15u) == 0u) {
+      const cudaError_t q = cudaStreamQuery(rs);
+      if (q == cudaSuccess) kernelsDone = true;                  // everything is rendered: copy what is left
+      else if (q != cudaErrorNotReady) throw CudaFailure{q, "cudaStreamQuery(render stream)", __FILE__, __LINE__};
+    }
+  }
+  cudaEvent_t copyEnd = nullptr;
+  if (timelineS) { CU(cudaEventCreate(&copyEnd)); CU(cudaEventRecord(copyEnd, cp)); }
+  unsigned long long c[3];
+  CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
+  CU(cudaStreamSynchronize(rs));
+  CU(cudaStreamSynchronize(cp));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+  scene->lastHostGpuMs = ms;
+  if (timelineS) {
+    float tc = 0;
+    CU(cudaEventElapsedTime(&tc, scene->ev0, copyEnd));
+    cudaEventDestroy(copyEnd);
+    fprintf(stderr, "[yahr_b200 timeline] streamed rows: wall %.3f ms; render %.3f copy end %.3f; %u rows, %u flagged "
+            "before the kernels ended, %u copies\n", nowMs() - w0, ms, tc, nRowsS, flaggedRows, nCopies);
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
+    stats->gpu_ms = ms;
+    if (ts.n) {
+      for (int k = 0; k < 3; ++k) {
+        float pm = 0;
+        CU(cudaEventElapsedTime(&pm, scene->phaseEv[k], scene->phaseEv[k + 1]));
+        stats->phase_ms[k] = pm;
+      }
+    }
+    stats->launches = launches;
+    stats->tiles = ts.n;
+    stats->h2d_bytes = sizeof(WavefrontParams) * (uint64_t)launches;
+    stats->d2h_bytes = d2h;
+    stats->wall_ms = nowMs() - w0;
+  }
+}
+
 static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
                       float* rgb_out, unsigned char* rgb8_out, uint32_t* primid_out, yahr_stats* stats,
                       int shardIndex = 0, int shardCount = 1) {
@@ -912,12 +1040,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     // on a caller stream
     CU(cudaDeviceSynchronize());
 
-    // STREAMED ROWS (one light slot, 1 spp, float frame -- the reference's own configuration).  The whole share is ONE
-    // launch of the wavefront set; the kernels count finalised pixels per row of the tile grid and publish a completed
-    // row in mapped host memory (wavefront.cu, rowsSignal); this thread polls the flags and starts the device-to-host
-    // copy of every completed row at once, so the copy engine runs under the traversal at row granularity and the
-    // persistent kernels pay their ramp-up and tail once (bands: once per band).  If the kernels end before every flag
-    // has been seen the remaining rows are simply copied then, so the accounting can never lose a row.
+    // Output strategy: the copy-engine bands below, or the streamed rows (renderStreamedRows).
     // Which of the two wins depends on the scene (the fused kernel's any-hit walks run with the probe-emitting lanes
     // only): the entry MEASURES it.  Per (image size, shard) the first two calls use the bands, the next two the
     // streamed rows, and from then on the faster one (wall time of the second call of each pair; the frames are
@@ -933,120 +1056,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         useStream = strategy->calls < 2 ? false : (strategy->calls < 4 ? true : strategy->msStream < strategy->msBands);
       }
       if (useStream) {
-        static const bool timelineS = getenv("YAHR_B200_TIMELINE") != nullptr;
-        if (nRowsS > scene->rowCap) {
-          cudaFree(scene->d_rowDone); scene->d_rowDone = nullptr;
-          if (scene->h_rowFlags) cudaFreeHost(scene->h_rowFlags);
-          scene->h_rowFlags = nullptr; scene->rowCap = 0;
-          CU(cudaMalloc(&scene->d_rowDone, nRowsS * sizeof(uint32_t)));
-          CU(cudaHostAlloc((void**)&scene->h_rowFlags, nRowsS * sizeof(uint32_t), cudaHostAllocMapped));
-          std::memset(scene->h_rowFlags, 0, nRowsS * sizeof(uint32_t));
-          CU(cudaHostGetDevicePointer((void**)&scene->d_rowFlags, scene->h_rowFlags, 0));
-          scene->rowCap = nRowsS; scene->rowSeq = 0;
-        }
-        if (++scene->rowSeq == 0u) {                                    // sequence wrapped: start over with clean flags
-          std::memset(scene->h_rowFlags, 0, scene->rowCap * sizeof(uint32_t));
-          scene->rowSeq = 1u;
-        }
-        const uint32_t seq = scene->rowSeq;
-        plan.W.rowOfV = ts.d_rowOfV; plan.W.rowItems = ts.d_rowItems; plan.W.rowDone = scene->d_rowDone;
-        plan.W.rowFlags = scene->d_rowFlags; plan.W.rowSeq = seq;
-        // rows complete in item order only when every batch is final at once: the fused kernel (with the two-kernel set
-        // every lit row completes in the shadow phase, after the whole primary trace)
-        if (const char* f = getenv("YAHR_B200_HOST_FUSED")) plan.W.fused = (uint32_t)atoi(f) & 3u;
-        else plan.W.fused = 1u;
-        uint32_t launches = 0;
-        CU(cudaMemsetAsync(scene->d_rowDone, 0, nRowsS * sizeof(uint32_t), rs));
-        CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
-        CU(cudaEventRecord(scene->ev0, rs));
-        enqueueTiles(scene, plan, 0, ts.n, rs, &launches, scene->phaseEv);
-        CU(cudaEventRecord(scene->ev1, rs));
-        uint64_t d2h = 0;
-        uint32_t nCopies = 0;
-        const size_t rowBytes = (size_t)W_ * 3 * sizeof(float), idBytes = (size_t)W_ * sizeof(uint32_t);
-        auto copyRows = [&](uint32_t r, uint32_t e) {
-          const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
-          CU(cudaMemcpyAsync((char*)rgb_out + (size_t)y0 * rowBytes, (const char*)scene->d_rgb + (size_t)y0 * rowBytes,
-                             (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
-          d2h += (uint64_t)(y1 - y0) * rowBytes;
-          if (primid_out) {
-            CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
-                               (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
-            d2h += (uint64_t)(y1 - y0) * idBytes;
-          }
-          ++nCopies;
-        };
-        // Copy issue policy.  Every copy costs ~5 us of copy-engine idle time whatever its size, so while the engine
-        // has work queued a short run of finished rows waits for its neighbours (rows finish roughly in order) and
-        // the copies grow exactly when the engine is the bottleneck; when it is about to run dry, whatever is ready
-        // goes out at once.  The engine's backlog is MODELLED (bytes queued at 48 GB/s + 8 us per copy), not queried: events between
-        // the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
-        const volatile uint32_t* flags = scene->h_rowFlags;
-        std::vector<unsigned char> issued(nRowsS, 0);
-        uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
-        // a run that has grown to this size goes out even when the engine has work
-        const uint64_t maxHeldBytes = getenv("YAHR_B200_STREAM_MAX_HELD_KB")
-                                          ? (uint64_t)atoi(getenv("YAHR_B200_STREAM_MAX_HELD_KB")) << 10 : (uint64_t)6 << 20;
-        double busyUntil = 0.0;                                         // ms on the nowMs() clock
-        bool kernelsDone = false;
-        while (nIssued < nRowsS) {
-          bool progress = false;
-          while (lowest < nRowsS && issued[lowest]) ++lowest;
-          for (uint32_t r = lowest; r < nRowsS;) {
-            if (issued[r] || !(kernelsDone || flags[r] == seq)) { ++r; continue; }
-            uint32_t e = r + 1;
-            while (e < nRowsS && !issued[e] && (kernelsDone || flags[e] == seq) && ts.rowY[e].x == ts.rowY[e - 1].y) ++e;
-            const uint64_t bytes = (uint64_t)(ts.rowY[e - 1].y - ts.rowY[r].x) * rowBytes;
-            const bool canGrow = e < nRowsS && !issued[e] && ts.rowY[e].x == ts.rowY[e - 1].y;     // row e is not finished yet
-            const double now = nowMs();
-            if (!kernelsDone && canGrow && bytes < maxHeldBytes && busyUntil - now > 0.05) { r = e; continue; }
-            copyRows(r, e);
-            busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 48.0e6 + 0.008;    // measured under load
-            if (!kernelsDone) flaggedRows += e - r;
-            for (uint32_t k = r; k < e; ++k) issued[k] = 1;
-            nIssued += e - r;
-            progress = true;
-            r = e;
-          }
-          if (!progress && !kernelsDone && (++spins & 15u) == 0u) {
-            const cudaError_t q = cudaStreamQuery(rs);
-            if (q == cudaSuccess) kernelsDone = true;                  // everything is rendered: copy what is left
-            else if (q != cudaErrorNotReady) throw CudaFailure{q, "cudaStreamQuery(render stream)", __FILE__, __LINE__};
-          }
-        }
-        cudaEvent_t copyEnd = nullptr;
-        if (timelineS) { CU(cudaEventCreate(&copyEnd)); CU(cudaEventRecord(copyEnd, cp)); }
-        unsigned long long c[3];
-        CU(cudaMemcpyAsync(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost, rs));
-        CU(cudaStreamSynchronize(rs));
-        CU(cudaStreamSynchronize(cp));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
-        scene->lastHostGpuMs = ms;
-        if (timelineS) {
-          float tc = 0;
-          CU(cudaEventElapsedTime(&tc, scene->ev0, copyEnd));
-          cudaEventDestroy(copyEnd);
-          fprintf(stderr, "[yahr_b200 timeline] streamed rows: wall %.3f ms; render %.3f copy end %.3f; %u rows, %u flagged "
-                  "before the kernels ended, %u copies\n", nowMs() - w0, ms, tc, nRowsS, flaggedRows, nCopies);
-        }
-        if (stats) {
-          std::memset(stats, 0, sizeof(*stats));
-          stats->n_primary = c[0]; stats->n_shadow = c[1]; stats->n_secondary = c[2];
-          stats->gpu_ms = ms;
-          if (ts.n) {
-            for (int k = 0; k < 3; ++k) {
-              float pm = 0;
-              CU(cudaEventElapsedTime(&pm, scene->phaseEv[k], scene->phaseEv[k + 1]));
-              stats->phase_ms[k] = pm;
-            }
-          }
-          stats->launches = launches;
-          stats->tiles = ts.n;
-          stats->h2d_bytes = sizeof(WavefrontParams) * (uint64_t)launches;
-          stats->d2h_bytes = d2h;
-          stats->wall_ms = nowMs() - w0;
-        }
+        renderStreamedRows(scene, plan, rgb_out, primid_out, stats, shardCount, w0);
         if (strategy) strategy->record(true, nowMs() - w0);
         return YAHR_OK;
       }
