@@ -288,6 +288,7 @@ def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch)
     torch = torch_mod()
     sc, _ = scenes.c2_bunny_proxy(384, 216, nu=40, nv=20)
     s = api.Scene(sc)
+    monkeypatch.setenv("YAHR_B200_POISON_FRAME", "1")      # a row copied before its pixels landed would carry NaN
     for (w, h) in [(384, 216), (517, 389), (33, 70), (384, 216)]:
         _, cam = scenes.c2_bunny_proxy(w, h, nu=40, nv=20)
         dev = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
@@ -323,6 +324,27 @@ def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch)
         assert np.array_equal(b_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(b_pid, rpid)
         assert st["launches"] < b_st["launches"] or h < 40       # one launch of the kernel set instead of one per band
         assert st["d2h_bytes"] == b_st["d2h_bytes"] == w * h * 16
+    s.close()
+
+
+def test_streamed_rows_full_size_stress(monkeypatch):
+    """BASELINE config C4 at full size through the streamed-row path, 40 frames with the device frame poisoned before
+    every call: every frame must equal the device-resident render bit for bit (a tile row published before all its
+    pixel stores had landed would show up as NaN)."""
+    torch = torch_mod()
+    sc, cam = scenes.c4_terrain()
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    dev = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    s.render_device(cam, dev.data_ptr(), None)
+    ref = dev.cpu().numpy().view(np.uint32)
+    pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+    monkeypatch.setenv("YAHR_B200_POISON_FRAME", "1")
+    monkeypatch.setenv("YAHR_B200_HOST_STREAM", "1")
+    for rep in range(40):
+        pinned.fill_(float("nan"))
+        s.render(cam, want_primid=False, out=(pinned.numpy(), None))
+        assert np.array_equal(pinned.numpy().view(np.uint32), ref), "frame %d differs" % rep
     s.close()
 
 

@@ -1039,6 +1039,12 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     // the scratch queues are shared with yahr_b200_render_device calls that may still be in flight
     // on a caller stream
     CU(cudaDeviceSynchronize());
+    // test hook: the device frame persists between calls, so a row copied before its pixels have landed would go
+    // unnoticed when the same frame is rendered twice; YAHR_B200_POISON_FRAME=1 fills it with NaN first
+    if (getenv("YAHR_B200_POISON_FRAME")) {
+      CU(cudaMemset(scene->d_rgb, 0xFF, (size_t)W_ * H_ * 3 * sizeof(float)));
+      if (primid_out) CU(cudaMemset(scene->d_primid, 0xEE, (size_t)W_ * H_ * sizeof(uint32_t)));
+    }
 
     // Output strategy: the copy-engine bands below, or the streamed rows (renderStreamedRows).
     // Which of the two wins depends on the scene (the fused kernel's any-hit walks run with the probe-emitting lanes
