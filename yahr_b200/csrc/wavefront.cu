@@ -712,6 +712,8 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
 // CTA is scheduled in the first wave and pulls work until the queue is empty.
 static void launchPersistent(void (*kernel)(WavefrontParams), const WavefrontParams& W, int numSMs,
                              cudaStream_t stream) {
+  // (asking for the smallest shared-memory carve-out instead of the driver's default 32 KB: primary unchanged, shadow
+  // kernel 0.426 -> 0.453 ms; not done.  profiles/r1ab section 7)
   int perSM = 0;
   if (W.blocksPerSM) perSM = (int)W.blocksPerSM;
   else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 128, 0) != cudaSuccess || perSM < 1) perSM = 8;
