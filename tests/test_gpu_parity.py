@@ -218,6 +218,49 @@ def test_parity_recursion_depth(depth):
     compare(rgb, pid, orgb, opid, 1.0, "c1 depth %d" % depth)
     assert st["n_secondary"] == ost["n_secondary"]
     assert st["n_shadow"] == ost["n_shadow"]
+    # the host-buffer entry: depth 3 with the one point light goes through the recursion kernel (k_wf_fused_depth)
+    hrgb, hpid, hst = outs["host"]
+    compare(hrgb, hpid, orgb, opid, 1.0, "c1 depth %d, host entry" % depth)
+    assert hst["n_secondary"] == ost["n_secondary"] and hst["n_shadow"] == ost["n_shadow"]
+
+
+@pytest.mark.parametrize("name", ["c1", "bunny", "grid", "terrain", "adversarial", "degenerate", "bunny-depth6"])
+def test_recursion_kernel_equals_megakernel(name):
+    """recursionDepth >= 2 with one point light: the per-batch wavefront kernel (k_wf_fused_depth, the default) against
+    the megakernel: same primitive IDs, same ray counts, bit-identical radiance (NaN pixels in the same places), on the
+    device-resident frame, through the host-buffer entry (bands and streamed rows) and against the oracle."""
+    torch = torch_mod()
+    sc, cam = SMALL[name]()
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    o = ob.OracleScene(sc)
+
+    def same(a, b):
+        na, nb = np.isnan(a), np.isnan(b)
+        return np.array_equal(na, nb) and np.array_equal(np.where(na, 0, a).view(np.uint32), np.where(nb, 0, b).view(np.uint32))
+
+    for depth in (2, 3, 5):
+        frames = {}
+        for kernel in (1, 2, 0):
+            d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
+            d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
+            st = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, kernel=kernel)
+            frames[kernel] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st)
+        assert frames[0][2]["launches"] == frames[2][2]["launches"] != frames[1][2]["launches"], "default is the recursion kernel"
+        for k in (2, 0):
+            assert np.array_equal(frames[k][1], frames[1][1]), "%s depth %d: primitive IDs" % (name, depth)
+            assert same(frames[k][0], frames[1][0]), "%s depth %d: radiance" % (name, depth)
+            for key in ("n_primary", "n_shadow", "n_secondary"):
+                assert frames[k][2][key] == frames[1][2][key], key
+        for _ in range(4):                       # host-buffer entry: bands twice, then streamed rows
+            rgb, pid, _ = s.render(cam, recursion_depth=depth)
+            assert np.array_equal(pid, frames[1][1]) and same(rgb, frames[1][0])
+        if depth == 3:
+            orgb, opid, _, ost = o.render(cam, recursion_depth=depth)
+            compare(frames[2][0], frames[2][1], orgb, opid, 1.0, "%s depth %d vs oracle" % (name, depth))
+            assert frames[2][2]["n_secondary"] == ost["n_secondary"] and frames[2][2]["n_shadow"] == ost["n_shadow"]
+    o.close()
+    s.close()
 
 
 def test_parity_spp_extension():

@@ -271,9 +271,15 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     return fail(YAHR_ERR_INVALID_ARGUMENT, "unknown traversal mode");
   // kernel selection: 0 = default (wavefront set for direct lighting, megakernel for recursion
   // depth != 1), 1 = megakernel, 2 = wavefront
-  plan.wavefront = opts->kernel == 2 || (opts->kernel == 0 && opts->recursion_depth == 1);
-  if (opts->kernel == 2 && opts->recursion_depth != 1)
-    return fail(YAHR_ERR_INVALID_ARGUMENT, "the wavefront kernel set handles recursion_depth 1 only");
+  // recursion depth >= 2 has a per-batch wavefront kernel for the reference's usual scene shape: ONE point light, no
+  // area lights, 4-wide tree, reference traversal order (k_wf_fused_depth); everything else recursive is the megakernel
+  const bool depthKernel = opts->recursion_depth >= 2 && sc->dev.nLights == 1 && sc->dev.nAreaLights == 0 &&
+                           sc->dev.nSlots == 1 && sc->dev.wide != nullptr && opts->traversal == YAHR_TRAVERSAL_REFERENCE &&
+                           !getenv("YAHR_B200_NO_DEPTH_KERNEL");
+  plan.wavefront = opts->kernel == 2 || (opts->kernel == 0 && (opts->recursion_depth == 1 || depthKernel));
+  if (opts->kernel == 2 && opts->recursion_depth != 1 && !depthKernel)
+    return fail(YAHR_ERR_INVALID_ARGUMENT,
+                "the wavefront kernels handle recursion_depth 1, or >= 2 with one point light and no area lights");
 
   // reserved[1] = 1: tile_stride / tile_offset count whole ROWS of the tile grid (host-buffer shards)
   const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset,

@@ -612,6 +612,131 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Whitted recursion (recursionDepth >= 2, Integrators.hs:22-47) for ONE point light, on the same plan as k_wf_fused: a
+// warp takes a batch through level after level -- closest-hit walk, shading, any-hit walk of the level's shadow probe,
+// then the mirror ray r = u - 2 (u . n) n from x + 0.001 r -- with ONE copy of the walk code for all of them, and
+// folds the levels at the end exactly as the megakernel does: acc = weight[k] * acc + direct[k] from the deepest level
+// up, weight = (n . r) @* f r, direct = 0 + contribution (sum = foldl (+) 0), a miss ends the path (Nothing -> 0).
+// The scene shipped with the reference uses depth 3, its Blender exporter depth 2 (scene.yahrr:2, render_engine.py:65).
+struct LevelShade {
+  V3 weight, nextOrigin, nextDir;          // ((n . r) @* f r), mirror ray
+  V3 probeOrigin, probeDir, contrib;       // shadow probe of the point light and what it contributes when unoccluded
+  float probeTMax;
+  bool hit, emit;
+};
+
+__device__ __forceinline__ void shadeLevel(const WavefrontParams& W, bool alive, const Ray& r, float tHit, uint32_t idx,
+                                           bool writeId, uint32_t pixel, LevelShade& o) {
+  const DeviceScene& sc = W.base.sc;
+  o.hit = alive && idx != kNoHit;
+  o.emit = false;
+  if (!o.hit) {
+    if (alive && writeId && W.base.primid) W.base.primid[pixel] = kNoHit;
+    return;
+  }
+  const Surface surf = surfaceAt(sc, idx, r, tHit);
+  if (writeId && W.base.primid) W.base.primid[pixel] = surf.primId;
+  const MaterialD mat = loadMaterial(sc, surf.material);
+  const Frame fr = makeFrame(surf);
+  const V3 wo = vneg(r.d);
+  const V3 refl = vsub(r.d, vscale(2.0f * dot(r.d, surf.n), surf.n));          // reflectionDir
+  o.weight = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
+  o.nextOrigin = vadd(surf.x, vscale(0.001f, refl));
+  o.nextDir = refl;
+  // directIllumination / illuminationAtPoint for the one point light (same expressions as shadeAndEmit's slot)
+  const V3 lightPos = xyz(__ldg(&sc.lights[0])), spectrum = xyz(__ldg(&sc.lights[1]));
+  const V3 pointToLight = vsub(lightPos, surf.x);
+  const V3 lightDir = vnorm(pointToLight);
+  const V3 k = bsdfAt(mat, fr, lightDir, wo);
+  if (lensq(k) > 0.0f) {
+    o.emit = true;
+    o.probeOrigin = vadd(surf.x, vscale(0.001f, lightDir));
+    const V3 dl = vsub(lightPos, o.probeOrigin);
+    o.probeDir = vnorm(dl);
+    o.probeTMax = len(dl);
+    const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
+    o.contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
+  }
+}
+
+constexpr int kMaxLevels = 16;             // YAHR_B200_MAX_RECURSION
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid_constant__ WavefrontParams W) {
+  uint2 stack[64];
+  V3 weight[kMaxLevels], direct[kMaxLevels];
+  const unsigned lane = threadIdx.x & 31u;
+  const int depth = W.base.depth;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[0], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= W.itemsPadded * W.samplesPerLaunch) break;
+    const uint32_t sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+    const uint32_t item = base - sLocal * W.itemsPadded + lane;
+    const bool valid = item < W.nItems;
+    int u = 0, v = 0;
+    Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    bool busy = false;
+    if (valid) {
+      itemPixel(W, item, u, v);
+      r = itemRay(W, u, v, W.sample + sLocal);
+      busy = travBegin(W.base.sc, r, 1e6f, s);
+    }
+    const uint32_t pixel = (uint32_t)(W.base.width * v + u);
+    const bool firstSample = W.sample + sLocal == 0u;
+    bool alive = valid;                    // the path of this lane still continues
+    int levels = 0;                        // levels recorded in weight[] / direct[]
+    uint32_t nProbes = 0, nSecondary = 0;
+    LevelShade ls;
+    ls.hit = false; ls.emit = false; ls.probeTMax = 0.0f;
+    ls.weight = ls.nextOrigin = ls.probeOrigin = ls.contrib = mk(0, 0, 0);
+    ls.nextDir = ls.probeDir = mk(0, 0, 1);
+#pragma unroll 1
+    for (int step = 0; step < 2 * depth; ++step) {
+      const bool anyPhase = (step & 1) != 0;
+      const int level = step >> 1;
+      if (!anyPhase && !__any_sync(kFull, alive)) break;
+      traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, anyPhase);
+      if (!anyPhase) {
+        shadeLevel(W, alive, r, s.tMax, s.best, level == 0 && firstSample, pixel, ls);
+        alive = ls.hit;
+        if (alive) weight[level] = ls.weight;
+        if (ls.emit) { r = makeRay(ls.probeOrigin, ls.probeDir); ++nProbes; }
+        s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+        busy = ls.emit && travBegin(W.base.sc, r, ls.probeTMax, s);
+      } else {
+        if (alive) {
+          const bool lit = ls.emit && s.best == kNoHit;
+          direct[level] = vadd(mk(0.0f, 0.0f, 0.0f), lit ? ls.contrib : mk(0.0f, 0.0f, 0.0f));
+          levels = level + 1;
+        }
+        alive = alive && level + 1 < depth;
+        s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+        busy = false;
+        if (alive) {
+          r = makeRay(ls.nextOrigin, ls.nextDir);
+          busy = travBegin(W.base.sc, r, 1e6f, s);
+          ++nSecondary;
+        }
+      }
+    }
+    if (valid) {
+      V3 acc = mk(0.0f, 0.0f, 0.0f);
+      for (int k = levels - 1; k >= 0; --k) acc = vadd(vmul(weight[k], acc), direct[k]);
+      float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
+      out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;
+    }
+    if (W.rowFlags) rowsSignal(W, valid ? (uint32_t)W.rowOfV[v] : 0u, valid, lane);       // streamed host output
+    const uint32_t wp = __reduce_add_sync(kFull, nProbes), ws = __reduce_add_sync(kFull, nSecondary);
+    if (lane == 0 && wp) atomicAdd(&W.work[3], wp);
+    if (lane == 0 && ws) atomicAdd(&W.work[4], ws);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   uint2 stack[64];
@@ -704,8 +829,9 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   // ray counters for the stats: primary = items, shadow = probes emitted
   atomicAdd(&W.base.counters[0], (unsigned long long)W.nItems * W.samplesPerLaunch);
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
+  atomicAdd(&W.base.counters[2], (unsigned long long)W.work[4]);
   if (W.bandStat) *W.bandStat += W.work[3];
-  W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0;      // ready for the next launch
+  W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0; W.work[4] = 0;      // ready for the next launch
 }
 
 // Persistent launch: exactly as many 128-thread CTAs as can be resident (occupancy API), so that every
@@ -737,6 +863,16 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
     // AREA: the scene has area lights (extension); kept out of the default instantiation
     const bool area = W.base.sc.nAreaLights != 0;
+    if (W.base.depth != 1) {
+      // recursion: the per-batch kernel (planFrame admits it only for one point light on the 4-wide tree)
+      launchPersistent(k_wf_fused_depth<6>, W, numSMs, stream);
+      if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
+      if (launches) *launches += 1;
+      if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
+      k_wf_count<<<1, 1, 0, stream>>>(W);
+      if (launches) *launches += 1;
+      continue;
+    }
     const bool fused = wide && !area && !W.dense && W.fused;
     if (fused) {
       if (W.fused & 2u) launchPersistent(k_wf_fused<7>, W, numSMs, stream);     // experiment: 72 registers
