@@ -224,27 +224,30 @@ def test_parity_recursion_depth(depth):
     assert hst["n_secondary"] == ost["n_secondary"] and hst["n_shadow"] == ost["n_shadow"]
 
 
-@pytest.mark.parametrize("name", ["c1", "bunny", "grid", "terrain", "adversarial", "degenerate", "bunny-depth6"])
+def test_recursion_kernel_is_for_point_lights_only():
+    """Area lights (extension) with recursion stay on the megakernel; asking for the wavefront kernels is an error."""
+    torch = torch_mod()
+    sc, cam = SMALL["bunny-area"]()
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    d_rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    with pytest.raises(api.YahrError):
+        s.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=2)
+    a = s.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=0)
+    b = s.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=1)
+    assert a["launches"] == b["launches"]
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "bunny", "grid", "terrain", "adversarial", "adversarial-sah", "degenerate",
+                                  "bunny-depth6"])
 def test_recursion_kernel_equals_megakernel(name):
-    """recursionDepth >= 2 with one point light: the per-batch wavefront kernel (k_wf_fused_depth, the default) against
-    the megakernel: same primitive IDs, same ray counts, bit-identical radiance (NaN pixels in the same places), on the
+    """recursionDepth >= 2 with point lights (one: k_wf_fused_depth, several: k_wf_fused_depth_lights -- the default):
+    the per-batch wavefront kernels against the megakernel: same primitive IDs, same ray counts, bit-identical radiance (NaN pixels in the same places), on the
     device-resident frame, through the host-buffer entry (bands and streamed rows) and against the oracle."""
     torch = torch_mod()
     sc, cam = SMALL[name]()
     w, h = api.image_size(cam)
-    if len(sc["lights"]) > 1:
-        # the recursion kernel is for ONE point light: with two the wavefront request is an error and the default is
-        # the megakernel; the rest of the test uses the first light only
-        s2 = api.Scene(sc)
-        d_rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
-        with pytest.raises(api.YahrError):
-            s2.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=2)
-        a = s2.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=0)
-        b = s2.render_device(cam, d_rgb.data_ptr(), None, recursion_depth=2, kernel=1)
-        assert a["launches"] == b["launches"]
-        s2.close()
-        sc = dict(sc)
-        sc["lights"] = sc["lights"][:1]
     s = api.Scene(sc)
     o = ob.OracleScene(sc)
 

@@ -271,15 +271,17 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     return fail(YAHR_ERR_INVALID_ARGUMENT, "unknown traversal mode");
   // kernel selection: 0 = default (wavefront set for direct lighting, megakernel for recursion
   // depth != 1), 1 = megakernel, 2 = wavefront
-  // recursion depth >= 2 has a per-batch wavefront kernel for the reference's usual scene shape: ONE point light, no
-  // area lights, 4-wide tree, reference traversal order (k_wf_fused_depth); everything else recursive is the megakernel
-  const bool depthKernel = opts->recursion_depth >= 2 && sc->dev.nLights == 1 && sc->dev.nAreaLights == 0 &&
-                           sc->dev.nSlots == 1 && sc->dev.wide != nullptr && opts->traversal == YAHR_TRAVERSAL_REFERENCE &&
+  // recursion depth >= 2 has per-batch wavefront kernels for the reference's own scene shape: point lights only (area
+  // lights are the extension), 4-wide tree, reference traversal order (k_wf_fused_depth*); everything else recursive is
+  // the megakernel
+  const bool depthKernel = opts->recursion_depth >= 2 && sc->dev.nLights >= 1 && sc->dev.nAreaLights == 0 &&
+                           sc->dev.nSlots == sc->dev.nLights && sc->dev.wide != nullptr &&
+                           opts->traversal == YAHR_TRAVERSAL_REFERENCE &&
                            !getenv("YAHR_B200_NO_DEPTH_KERNEL");
   plan.wavefront = opts->kernel == 2 || (opts->kernel == 0 && (opts->recursion_depth == 1 || depthKernel));
   if (opts->kernel == 2 && opts->recursion_depth != 1 && !depthKernel)
     return fail(YAHR_ERR_INVALID_ARGUMENT,
-                "the wavefront kernels handle recursion_depth 1, or >= 2 with one point light and no area lights");
+                "the wavefront kernels handle recursion_depth 1, or >= 2 with point lights only (no area lights)");
 
   // reserved[1] = 1: tile_stride / tile_offset count whole ROWS of the tile grid (host-buffer shards)
   const TileSet& ts = tilesFor(sc, cs.width, cs.height, opts->tile_stride, opts->tile_offset,
@@ -355,8 +357,9 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
   const TileSet& ts = *plan.ts;
   if (plan.wavefront) {
     WavefrontParams W = plan.W;
-    const size_t entries = (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) * plan.entriesPerItem *
-                           plan.samplesPerLaunch;
+    // (the recursion kernels keep their probes in registers: no queue)
+    const size_t entries = plan.P.depth != 1 ? 0 : (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) *
+                                                       plan.entriesPerItem * plan.samplesPerLaunch;
     if (entries > sc->wfEntries[slot]) {          // grows only on the first frame of a given size
       CU(cudaDeviceSynchronize());
       cudaFree(sc->wfQ0[slot]); cudaFree(sc->wfQ1[slot]); cudaFree(sc->wfQ2[slot]); cudaFree(sc->wfVis[slot]);

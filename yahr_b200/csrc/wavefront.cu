@@ -736,6 +736,112 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid
   }
 }
 
+// The same for SEVERAL point lights: a level is one closest-hit walk and one any-hit walk per light, in light order
+// (directIllumination's sum = foldl (+) 0 over the lights, Integrators.hs:50-61).  Between the walks of a level only
+// (ray, primitive, t) of the hit is kept; the surface, frame and material are rebuilt from them before each probe.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const __grid_constant__ WavefrontParams W) {
+  uint2 stack[64];
+  V3 weight[kMaxLevels], direct[kMaxLevels];
+  const unsigned lane = threadIdx.x & 31u;
+  const DeviceScene& sc = W.base.sc;
+  const int depth = W.base.depth;
+  const int nL = (int)sc.nLights, per = 1 + nL;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[0], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= W.itemsPadded * W.samplesPerLaunch) break;
+    const uint32_t sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+    const uint32_t item = base - sLocal * W.itemsPadded + lane;
+    const bool valid = item < W.nItems;
+    int u = 0, v = 0;
+    Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    bool busy = false;
+    if (valid) {
+      itemPixel(W, item, u, v);
+      r = itemRay(W, u, v, W.sample + sLocal);
+      busy = travBegin(sc, r, 1e6f, s);
+    }
+    const uint32_t pixel = (uint32_t)(W.base.width * v + u);
+    const bool firstSample = W.sample + sLocal == 0u;
+    bool alive = valid, emit = false;
+    int levels = 0;
+    uint32_t nProbes = 0, nSecondary = 0, hitIdx = kNoHit;
+    float hitT = 0.0f;
+    V3 lo = r.o, ld = r.d;                       // the ray of the current level
+    V3 total = mk(0, 0, 0), contrib = mk(0, 0, 0);
+#pragma unroll 1
+    for (int step = 0; step < depth * per; ++step) {
+      const int level = step / per, phase = step - level * per;      // phase 0: closest hit; 1..nL: probe of light phase-1
+      if (phase == 0 && !__any_sync(kFull, alive)) break;
+      traverseWarpWide<false>(sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, phase != 0);
+      if (phase == 0) {
+        const bool hit = alive && s.best != kNoHit;
+        if (alive && !hit && level == 0 && firstSample && W.base.primid) W.base.primid[pixel] = kNoHit;
+        alive = hit; hitIdx = s.best; hitT = s.tMax;
+        total = mk(0.0f, 0.0f, 0.0f);
+      } else if (alive) {
+        const bool lit = emit && s.best == kNoHit;
+        total = vadd(total, lit ? contrib : mk(0.0f, 0.0f, 0.0f));
+      }
+      // what the next walk of this lane is: the probe of light `phase`, or the mirror ray of the next level
+      emit = false; busy = false;
+      s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+      if (alive) {
+        const Ray lr = makeRay(lo, ld);
+        const Surface surf = surfaceAt(sc, hitIdx, lr, hitT);
+        const MaterialD mat = loadMaterial(sc, surf.material);
+        const Frame fr = makeFrame(surf);
+        const V3 wo = vneg(ld);
+        const V3 refl = vsub(ld, vscale(2.0f * dot(ld, surf.n), surf.n));          // reflectionDir
+        if (phase == 0) {
+          if (level == 0 && firstSample && W.base.primid) W.base.primid[pixel] = surf.primId;
+          weight[level] = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
+        }
+        if (phase < nL) {
+          const V3 lightPos = xyz(__ldg(&sc.lights[2 * phase + 0])), spectrum = xyz(__ldg(&sc.lights[2 * phase + 1]));
+          const V3 pointToLight = vsub(lightPos, surf.x);
+          const V3 lightDir = vnorm(pointToLight);
+          const V3 k = bsdfAt(mat, fr, lightDir, wo);
+          if (lensq(k) > 0.0f) {
+            emit = true;
+            const V3 p0 = vadd(surf.x, vscale(0.001f, lightDir));
+            const V3 dl = vsub(lightPos, p0);
+            r = makeRay(p0, vnorm(dl));
+            busy = travBegin(sc, r, len(dl), s);
+            const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
+            contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
+            ++nProbes;
+          }
+        } else {
+          direct[level] = total;
+          levels = level + 1;
+          alive = level + 1 < depth;
+          if (alive) {
+            lo = vadd(surf.x, vscale(0.001f, refl)); ld = refl;
+            r = makeRay(lo, ld);
+            busy = travBegin(sc, r, 1e6f, s);
+            ++nSecondary;
+          }
+        }
+      }
+    }
+    if (valid) {
+      V3 acc = mk(0.0f, 0.0f, 0.0f);
+      for (int k = levels - 1; k >= 0; --k) acc = vadd(vmul(weight[k], acc), direct[k]);
+      float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
+      out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;
+    }
+    if (W.rowFlags) rowsSignal(W, valid ? (uint32_t)W.rowOfV[v] : 0u, valid, lane);       // streamed host output
+    const uint32_t wp = __reduce_add_sync(kFull, nProbes), ws = __reduce_add_sync(kFull, nSecondary);
+    if (lane == 0 && wp) atomicAdd(&W.work[3], wp);
+    if (lane == 0 && ws) atomicAdd(&W.work[4], ws);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
@@ -864,8 +970,9 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     // AREA: the scene has area lights (extension); kept out of the default instantiation
     const bool area = W.base.sc.nAreaLights != 0;
     if (W.base.depth != 1) {
-      // recursion: the per-batch kernel (planFrame admits it only for one point light on the 4-wide tree)
-      launchPersistent(k_wf_fused_depth<6>, W, numSMs, stream);
+      // recursion: the per-batch kernels (planFrame admits them for point lights only, on the 4-wide tree)
+      if (W.base.sc.nLights == 1) launchPersistent(k_wf_fused_depth<6>, W, numSMs, stream);
+      else launchPersistent(k_wf_fused_depth_lights<6>, W, numSMs, stream);
       if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
       if (launches) *launches += 1;
       if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
