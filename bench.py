@@ -405,7 +405,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ----------------------------------------------------
     peak, peak_src = peaks()
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
-    bpr = BYTES_PER_RAY.get(args.workload)
+    # the oracle's per-ray byte counts (tools/bytes_per_ray.json) are for the configured workloads at depth 1, 1 spp
+    bpr = BYTES_PER_RAY.get(args.workload) if (args.depth == 1 and args.spp == 1) else None
     roofline = None
     if k_ms and bpr:
         achieved = rays_local * bpr / (k_ms * 1e-3) / 1e9
