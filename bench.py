@@ -325,9 +325,9 @@ def run_ours(args):
     if world == 1:
         host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
         out = (host_rgb.numpy(), None)
-        # the host-buffer entry measures its two output strategies during its first four calls per image size (copy-engine
+        # the host-buffer entry measures its two output strategies during its first six calls per image size (copy-engine
         # bands / streamed rows, capi.cu renderHost) and keeps the faster one: warm up past that
-        for _ in range(max(5, args.warmup)):
+        for _ in range(max(7, args.warmup)):
             _, _, ste = R.scene.render(cam, recursion_depth=args.depth, spp=args.spp, want_primid=False, out=out)
         times = []
         for _ in range(args.steps):
@@ -377,7 +377,7 @@ def run_ours(args):
         host = SharedHostFrame(w, h, rank, world, barrier=barrier)
         times = []
         ste = None
-        e2e_warmup = max(5, args.warmup)               # past the entry's four strategy-measuring calls (see above)
+        e2e_warmup = max(7, args.warmup)               # past the entry's six strategy-measuring calls (see above)
         for i in range(e2e_warmup + args.steps):
             flush.zero_()
             barrier()                                  # ranks leave the barrier together: a common start

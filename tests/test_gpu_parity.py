@@ -268,7 +268,7 @@ def test_recursion_kernel_equals_megakernel(name):
             assert same(frames[k][0], frames[1][0]), "%s depth %d: radiance" % (name, depth)
             for key in ("n_primary", "n_shadow", "n_secondary"):
                 assert frames[k][2][key] == frames[1][2][key], key
-        for _ in range(4):                       # host-buffer entry: bands twice, then streamed rows
+        for _ in range(5):                       # host-buffer entry: bands three times, then streamed rows
             rgb, pid, _ = s.render(cam, recursion_depth=depth)
             assert np.array_equal(pid, frames[1][1]) and same(rgb, frames[1][0])
         if depth == 3:
@@ -369,7 +369,7 @@ def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch)
             s.render_device(cam, fdev.data_ptr(), None, tune=tune)
             assert torch.equal(fdev.view(torch.int32), dev.view(torch.int32))
         pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
-        for rep in range(6):                   # unpinned strategy: two calls with the bands, two streamed, then the faster
+        for rep in range(8):                   # unpinned strategy: three calls with the bands, three streamed, then the faster
             rgb, pid, _ = s.render(cam)
             assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(pid, rpid)
         monkeypatch.setenv("YAHR_B200_HOST_STREAM", "1")

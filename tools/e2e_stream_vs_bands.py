@@ -43,7 +43,7 @@ def main():
             pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
             frame = pinned.numpy()
         results = {}
-        for mode in ("0", "1", "1f", "1q", "auto", "0", "1f", "auto"):
+        for mode in ("0", "1", "1f", "1q", "auto", "0", "1f", "auto", "auto"):
             if mode == "auto":                                   # the entry's own measured choice
                 os.environ.pop("YAHR_B200_HOST_STREAM", None)
                 os.environ.pop("YAHR_B200_HOST_FUSED", None)

@@ -83,14 +83,19 @@ struct TileSet {
 
 }  // namespace
 
-// Host-buffer entry: measured choice between the copy-engine bands and the streamed rows (renderHost).
+// Host-buffer entry: measured choice between the copy-engine bands and the streamed rows (renderHost).  Calls 0-2 of a
+// key use the bands, calls 3-5 the streamed rows; the first call of each kind is a warm-up (allocations, band order),
+// the faster of the other two counts.  The streamed rows are kept only when they win by more than 3 %.
 struct HostStrategy {
   int calls = 0;
-  double msBands = 0.0, msStream = 0.0;
+  double msBands = 1e30, msStream = 1e30;
+  bool exploring() const { return calls < 6; }
+  bool wantStream() const { return calls < 3 ? false : (calls < 6 ? true : msStream < 0.97 * msBands); }
   void record(bool streamed, double ms) {
-    if (calls == 1 && !streamed) msBands = ms;
-    if (calls == 3 && streamed) msStream = ms;
-    if (calls < 4) ++calls;
+    if (!exploring()) return;
+    if (!streamed && (calls == 1 || calls == 2) && ms < msBands) msBands = ms;
+    if (streamed && (calls == 4 || calls == 5) && ms < msStream) msStream = ms;
+    ++calls;
   }
 };
 
@@ -1057,9 +1062,9 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
 
     // Output strategy: the copy-engine bands below, or the streamed rows (renderStreamedRows).
     // Which of the two wins depends on the scene (the fused kernel's any-hit walks run with the probe-emitting lanes
-    // only): the entry MEASURES it.  Per (image size, shard) the first two calls use the bands, the next two the
-    // streamed rows, and from then on the faster one (wall time of the second call of each pair; the frames are
-    // bit-identical either way).  YAHR_B200_HOST_STREAM=0 / 1 pins the bands / the streamed rows.
+    // only): the entry MEASURES it.  Per (image size, shard) the first three calls use the bands, the next three the
+    // streamed rows, and from then on the faster one (HostStrategy; the frames are bit-identical either way).
+    // YAHR_B200_HOST_STREAM=0 / 1 pins the bands / the streamed rows.
     HostStrategy* strategy = nullptr;
     {
       const char* env = getenv("YAHR_B200_HOST_STREAM");
@@ -1068,7 +1073,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       if (useStream && env) useStream = atoi(env) != 0;
       else if (useStream) {
         strategy = &scene->hostStrategy[std::make_tuple(W_, H_, shardIndex, shardCount, primid_out ? 1 : 0)];
-        useStream = strategy->calls < 2 ? false : (strategy->calls < 4 ? true : strategy->msStream < strategy->msBands);
+        useStream = strategy->wantStream();
       }
       if (useStream) {
         renderStreamedRows(scene, plan, rgb_out, primid_out, stats, shardCount, w0);
