@@ -52,14 +52,12 @@ def main():
                 rank, label, " ".join("%.3f" % x for x in ts), st["gpu_ms"], st["wall_ms"], st["launches"], st["d2h_bytes"]),
                 flush=True)
 
-    copy_only = "copyonly" in sys.argv[1:]
-    if copy_only:
-        calls = lambda *a, **k: None                      # noqa: E731  (only the concurrent pure copies below)
-    calls("shared, all ranks", shared.array, None)
-    calls("private, all ranks", private.numpy(), None)
-    for r in range(min(world, 2)):
-        calls("shared, rank %d alone" % r, shared.array, r)
-        calls("private, rank %d alone" % r, private.numpy(), r)
+    if "copyonly" not in sys.argv[1:]:                    # "copyonly": just the concurrent pure copies below
+        calls("shared, all ranks", shared.array, None)
+        calls("private, all ranks", private.numpy(), None)
+        for r in range(min(world, 2)):
+            calls("shared, rank %d alone" % r, shared.array, r)
+            calls("private, rank %d alone" % r, private.numpy(), r)
 
     # pure copies of this rank's share (contiguous block of the same size)
     share = (h // world) * w * 3

@@ -888,7 +888,7 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
 // granularity and the persistent kernel pays its ramp-up and tail once (bands: once per band).  If the kernel ends
 // before every flag has been seen the remaining rows are simply copied then: the accounting can never lose a row.
 static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_out, uint32_t* primid_out, yahr_stats* stats,
-                               int shardCount, double w0) {
+                               double w0) {
   const TileSet& ts = *plan.ts;
   const uint32_t nRowsS = (uint32_t)ts.rowY.size();
   const int W_ = plan.cs.width;
@@ -939,8 +939,8 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
   // Copy issue policy.  Every copy costs ~5 us of copy-engine idle time whatever its size, so while the engine
   // has work queued a short run of finished rows waits for its neighbours (rows finish roughly in order) and
   // the copies grow exactly when the engine is the bottleneck; when it is about to run dry, whatever is ready
-  // goes out at once.  The engine's backlog is MODELLED (bytes queued at 48 GB/s + 8 us per copy), not queried: events between
-  // the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
+  // goes out at once.  The engine's backlog is MODELLED (bytes queued at 48 GB/s + 8 us per copy), not queried: events
+  // between the copies would serialise them.  Runs end at the gaps between a shard's blocks of rows.
   const volatile uint32_t* flags = scene->h_rowFlags;
   std::vector<unsigned char> issued(nRowsS, 0);
   uint32_t nIssued = 0, lowest = 0, spins = 0, flaggedRows = 0;
@@ -1076,7 +1076,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         useStream = strategy->wantStream();
       }
       if (useStream) {
-        renderStreamedRows(scene, plan, rgb_out, primid_out, stats, shardCount, w0);
+        renderStreamedRows(scene, plan, rgb_out, primid_out, stats, w0);
         if (strategy) strategy->record(true, nowMs() - w0);
         return YAHR_OK;
       }
