@@ -40,38 +40,35 @@ def _load_bytes_per_ray():
         return {}
 
 
-# Figures taken from the committed `ncu --set full` captures (profiles/*.json written by tools/ncu_summary.py from
-# the .ncu-rep of this same command): DRAM bytes per frame and what actually bounds the kernels.
-NCU_SUMMARIES = {("c4-terrain", "wavefront"): "profiles/r1r_ncu_full_wavefront_wide_c4terrain.json"}
-# the round-1a megakernel capture predates the JSON summaries (profiles/r1a_ncu_full_k_render_mega_c4terrain.txt)
-NCU_LEGACY = {("c4-terrain", "mega"): {"traffic": 98.76e6 + 58.22e6,
-                                       "bound_by": {"k_render_mega": {"issue_active": 0.50, "threads_per_inst": 17.96},
-                                                    "source": "profiles/r1a_ncu_full_k_render_mega_c4terrain.txt"}}}
+# `ncu --set full` capture of the default kernels on a workload, summarised by tools/ncu_summary.py from the .ncu-rep of
+# this same command.  It supplies the per-frame COUNTS that do not depend on timing -- executed warp instructions, L1
+# data-pipe wavefronts, DRAM bytes -- and bench.py turns them into live fractions with the kernel durations and the SM
+# clock it measures itself.  A capture is only trusted when its source fingerprint is the current tree's.
+NCU_SUMMARIES = {"c4-terrain": "profiles/r2_ncu_full_default_c4terrain.json"}
 
 
-def ncu_figures(workload_name, kernel_set):
-    """(dram bytes per frame, {kernel: issue / L1 / divergence figures}) from the committed capture, or (None, None)."""
-    key = (workload_name, kernel_set)
-    if key in NCU_LEGACY:
-        return NCU_LEGACY[key]["traffic"], NCU_LEGACY[key]["bound_by"]
-    path = NCU_SUMMARIES.get(key)
+def ncu_capture(workload_name):
+    """(capture dict, None) or (None, reason)."""
+    from yahr_b200 import api
+    path = NCU_SUMMARIES.get(workload_name)
     if not path:
-        return None, None
+        return None, "no ncu capture committed for this workload"
     try:
         js = json.load(open(os.path.join(ROOT, path)))
-    except Exception:
-        return None, None
-    traffic, by = 0.0, {"source": js.get("source", path)}
+    except Exception as e:
+        return None, "cannot read %s: %s" % (path, e)
+    fp = api.source_fingerprint()
+    if js.get("fingerprint") != fp:
+        return None, ("capture %s refused: it was taken on sources %s, the loaded library is built from %s"
+                      % (path, js.get("fingerprint"), fp))
+    by = {}
     for k in js["kernels"]:
-        traffic += k["dram_bytes"] or 0.0
-        short = k["name"].replace("void ", "").split("<")[0].split("(")[0]
-        if short == "k_wf_count":
-            continue
-        by[short] = {"issue_active": round(k["issue_active"] / 100.0, 3), "threads_per_inst": k["threads_per_inst"],
-                     "l1_lsu_wavefronts": round(k["l1_lsu_wavefronts_pct"] / 100.0, 3),
-                     "l1_hit": round(k["l1_hit"] / 100.0, 3), "l2_hit": round(k["l2_hit"] / 100.0, 3),
-                     "ms_under_ncu": k["ms"]}
-    return traffic, by
+        short = k["name"].replace("void ", "").split("<")[0].split("(")[0].split("::")[-1]
+        if short in ("k_wf_primary", "k_wf_shadow", "k_wf_fused"):
+            by[short] = k
+    if "k_wf_primary" not in by:
+        return None, "capture %s holds no k_wf_primary launch" % path
+    return {"path": path, "fingerprint": fp, "kernels": by}, None
 
 
 BYTES_PER_RAY = _load_bytes_per_ray()
@@ -222,6 +219,166 @@ def _host_cores():
         return os.cpu_count() or 1
 
 
+def build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clocks, launches_per_step, world, gpu_counts):
+    """The roofline object of the JSON line.  The traversal is irregular graph work served from L1 / L2 (real DRAM
+    traffic is a few % of the HBM peak), so the resource that binds is on the SM: instruction issue slots, or the L1
+    data pipe.  `frac` is the larger of the two for the dominant kernel (k_wf_primary), <= 1 by construction:
+        issue : warp instructions executed per launch / (4 schedulers x SMs x SM clock x kernel duration)
+        l1    : L1 data-pipe wavefronts per launch    / (1 per cycle x SMs x SM clock x kernel duration)
+    Counts come from the committed ncu capture of the same sources (refused when stale); durations and the clock
+    are measured live in this run.  The SURVEY 8(d) algorithmic-bytes figure is kept as `algorithmic`."""
+    import torch
+    peak, peak_src = peaks()
+    k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
+    wf = launches_per_step > 1
+    if not k_ms:
+        return None
+    ph = [float(x) for x in np.mean(np.asarray(phase_ms), axis=0)] if phase_ms else [k_ms, 0.0, 0.0, 0.0]
+    n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    share = rays_local / max(rays_total, 1.0)
+    default_run = args.depth == 1 and args.spp == 1 and args.kernel == 0 and args.tune == 0 and args.traversal == "reference"
+    cap, why = ncu_capture(args.workload) if (wf and default_run) else (None, "not the default kernel set / configuration")
+    kernels = {}
+    if cap:
+        for short, ms in (("k_wf_primary", ph[0]), ("k_wf_shadow", ph[2])):
+            k = cap["kernels"].get(short)
+            if not k or ms <= 0:
+                continue
+            cyc = ms * 1e-3 * mhz * 1e6
+            inst = (k.get("inst_executed") or 0.0) * share
+            wavef = (k.get("l1_lsu_wavefronts") or 0.0) * share
+            kernels[short] = {
+                "live_ms": ms, "ms_under_ncu": k["ms"],
+                "issue_frac": inst / (cyc * n_sm * 4.0), "l1_frac": wavef / (cyc * n_sm) if wavef else None,
+                "warp_inst_per_launch": inst, "l1_wavefronts_per_launch": wavef or None,
+                "threads_per_inst": k.get("threads_per_inst"), "l1_hit": k.get("l1_hit"), "l2_hit": k.get("l2_hit"),
+                "warps_active_pct": k.get("warps_active_pct"), "registers": k.get("registers"),
+                "dram_bytes_per_launch": k.get("dram_bytes") if world == 1 else None,
+                "hbm_frac_actual": (k["dram_bytes"] / (ms * 1e-3) / 1e9 / peak) if (world == 1 and k.get("dram_bytes")) else None,
+            }
+    bpr = BYTES_PER_RAY.get(args.workload) if (args.depth == 1 and args.spp == 1) else None
+    algorithmic = None
+    if bpr:
+        a = rays_local * bpr / (k_ms * 1e-3) / 1e9
+        algorithmic = {"bytes_per_ray": bpr, "achieved_gbs": a, "frac_of_hbm_peak": a / peak,
+                       "note": "SURVEY 8(d): every box / primitive fetch of every ray under the REFERENCE's traversal at "
+                               "32 B per box; the scene is cache-resident and the 4-wide walk skips ancestor boxes, so "
+                               "this is a work-rate figure, not an HBM fraction (it can exceed 1)"}
+    dom = kernels.get("k_wf_primary")
+    if dom:
+        bound = "issue" if dom["issue_frac"] >= (dom["l1_frac"] or 0.0) else "l1"
+        frac = dom["issue_frac"] if bound == "issue" else dom["l1_frac"]
+        achieved = (dom["warp_inst_per_launch"] if bound == "issue" else dom["l1_wavefronts_per_launch"]) / (dom["live_ms"] * 1e-3) / 1e9
+        rpeak = n_sm * (4.0 if bound == "issue" else 1.0) * mhz * 1e6 / 1e9
+        unit = "G warp-inst/s" if bound == "issue" else "G wavefronts/s"
+        traffic = sum(v["dram_bytes_per_launch"] or 0.0 for v in kernels.values()) if world == 1 else None
+    else:
+        bound, frac, achieved, rpeak, unit, traffic = "issue", None, None, n_sm * 4.0 * mhz * 1e6 / 1e9, "G warp-inst/s", None
+    return {"bound": bound, "achieved": achieved, "peak": rpeak, "unit": unit, "frac": frac, "traffic": traffic,
+            "kernel": "k_wf_primary (primary trace + shading, dominant); k_wf_shadow listed beside it" if wf else "k_render_mega",
+            "kernel_ms": k_ms, "phase_ms": {"primary_trace_and_shade": ph[0], "shadow_trace": ph[2]} if wf else None,
+            "peak_source": "%d SMs x %s per cycle x %.0f MHz (median SM clock sampled during this run)"
+                           % (n_sm, "4 issue slots" if bound == "issue" else "1 L1 wavefront", mhz),
+            "counts_source": (cap["path"] + " (fingerprint %s = current sources)" % cap["fingerprint"]) if cap else None,
+            "counts_refused": why, "kernels": kernels or None,
+            "hbm": {"peak_gbs": peak, "peak_source": peak_src, "traffic_bytes_per_frame": traffic,
+                    "frac_actual": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None},
+            "algorithmic": algorithmic, "gpu_counted": gpu_counts, "rays_per_launch": rays_local,
+            "note": "HBM is not the binding roofline of this path (irregular traversal served from L1/L2; see hbm.frac_actual): "
+                    "`frac` is the binding SM-side resource of the dominant kernel, counts from ncu on the same sources, "
+                    "durations and clock live.  DESIGN.md section 4."}
+
+
+def check_frames(R, sc, cam, args, trav, world, rank, barrier, host_frames):
+    """Not timed.  (i) N > 1: rank 0's assembled frame (the exchange `value` times) bit for bit against a single-GPU
+    render of the whole frame on rank 0 -- the reference's `concat` + scatter (main.hs:83,95,98-107) must not lose or
+    misplace a pixel; (ii) the host frames the e2e calls filled, against the same single-GPU frame; (iii) the
+    single-GPU frame against the CPU oracle on sampled reference tiles: primitive IDs bit-exact, radiance within the
+    north-star tolerance.  The oracle is the checker here, never the thing measured."""
+    import torch
+    from yahr_b200 import api
+    w, h = api.image_size(cam)
+    kw = dict(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
+    R.render(**kw)                                   # one more exchange: the frame to check
+    barrier()
+    out = None
+    if rank == 0:
+        full = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+        fpid = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        R.scene.render_device(cam, full.data_ptr(), fpid.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, **kw)
+        torch.cuda.synchronize()
+        out = {"n_gpus": world}
+        if world > 1:
+            out["vs_single_gpu"] = "bit-equal" if torch.equal(R.frame.view(torch.int32), full.view(torch.int32)) else "DIFFERS"
+        ref = full.cpu().numpy()
+        for name, a in host_frames.items():
+            if a.dtype == np.uint8:
+                same = np.array_equal(a, api.quantize_rgb8_host(ref))
+            else:
+                same = np.array_equal(a.view(np.uint32), ref.view(np.uint32))
+            out[name + "_vs_single_gpu"] = "bit-equal" if same else "DIFFERS"
+        if args.spp == 1 or args.check_oracle:
+            from oracle import binding as ob
+            n_tiles = int(api.num_batches(1, w, h))
+            stride = max(1, n_tiles // 96)
+            o = ob.OracleScene(sc)
+            orgb = np.full((h, w, 3), np.nan, np.float32)
+            opid = np.full((h, w), 0xFFFFFFFE, np.uint32)
+            _, _, _, ost = o.render(cam, recursion_depth=args.depth, spp=args.spp, tile_stride=stride, tile_offset=stride // 3,
+                                    out=(orgb, opid, np.zeros((h, w), np.float32)))
+            o.close()
+            sel = opid != 0xFFFFFFFE
+            pid = fpid.cpu().numpy().view(np.uint32)
+            a, b = ref[sel].astype(np.float64), orgb[sel].astype(np.float64)
+            nan = np.isnan(a) | np.isnan(b)
+            d = np.where(nan, 0.0, a - b)
+            out.update({"oracle_tiles": int(ost["tiles"]), "oracle_pixels": int(sel.sum()),
+                        "id_match": float((pid[sel] == opid[sel]).mean()),
+                        "nan_pixels_equal": bool(np.array_equal(np.isnan(a), np.isnan(b))),
+                        "max_abs_err": float(np.abs(d).max()), "rmse": float(np.sqrt((d ** 2).mean()))})
+    barrier()
+    return out
+
+
+def extra_workloads(args, world, rank, barrier):
+    """C5 as BASELINE.json names it -- 10 M triangles, 3840x2160, 64 spp, point + quad area light, tiles sharded over the
+    GPUs -- device-resident `value` only, a few frames (one frame is ~1.5 G rays)."""
+    import torch
+    import torch.distributed as dist
+    from yahr_b200.dist import TileShardedRenderer
+    sc, cam, desc = workload("c5-area")
+    spp = 64
+    R = TileShardedRenderer(sc, cam, mode=args.exchange)
+    st = R.stats_render(recursion_depth=1, spp=spp)
+    rays = torch.tensor([st["n_primary"] + st["n_shadow"] + st["n_secondary"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rays)
+    R.render(recursion_depth=1, spp=spp)
+    barrier()
+    steps = max(1, args.extra_steps)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        if world > 1:
+            dist.barrier()
+        ev[i][0].record()
+        R.render(recursion_depth=1, spp=spp)
+        ev[i][1].record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    info = R.scene.info()
+    mode = R.mode
+    R.close()
+    m = float(ms.mean())
+    return [{"name": "c5-area", "workload": desc.replace("run with --spp 64", "64 spp"), "spp": spp, "n_gpus": world,
+             "steps": steps, "ms_per_step": m, "value": float(rays) / (m * 1e-3) / 1e6, "unit": UNIT,
+             "rays_per_frame": float(rays), "exchange": mode, "scene_bytes": int(info["device_bytes"]),
+             "bvh_build_ms": info["build_ms"], "scaling": "strong",
+             "note": "area lights and spp > 1 are extensions (no reference counterpart): parity against the repo's own oracle"}]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -259,10 +416,13 @@ def run_ours(args):
     w, h = api.image_size(cam)
     trav = api.TRAVERSAL_ORDERED if args.traversal == "ordered" else api.TRAVERSAL_REFERENCE
 
+    barrier0 = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+    barrier0()                                         # process-group / context start-up is not scene creation
     t0 = time.time()
     R = TileShardedRenderer(sc, cam, mode=args.exchange)
     create_s = time.time() - t0
     info = R.scene.info()
+    exchange_mode = R.mode
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -322,12 +482,11 @@ def run_ours(args):
 
     # ---- e2e: host-buffer C-ABI call, pinned output, copies inside the timed region ----------
     e2e = None
+    host_frames = {}                                  # name -> numpy view of a host frame to check afterwards (rank 0)
     if world == 1:
         host_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
         out = (host_rgb.numpy(), None)
-        # the host-buffer entry measures its two output strategies during its first six calls per image size (copy-engine
-        # bands / streamed rows, capi.cu renderHost) and keeps the faster one: warm up past that
-        for _ in range(max(7, args.warmup)):
+        for _ in range(args.warmup):
             _, _, ste = R.scene.render(cam, recursion_depth=args.depth, spp=args.spp, want_primid=False, out=out)
         times = []
         for _ in range(args.steps):
@@ -349,6 +508,7 @@ def run_ours(args):
             if i >= max(1, args.warmup):
                 t8.append(time.perf_counter() - t)
         rgb8_ms = float(np.mean(t8)) * 1e3
+        host_frames = {"e2e_float": host_rgb.numpy(), "e2e_rgb8": host_rgb8.numpy()}
         # pure device-to-host copy of one frame from pinned memory, for scale
         dev_frame = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
         tc = []
@@ -364,12 +524,13 @@ def run_ours(args):
                "api": "yahr_b200_render (host buffers; kernel parameters up, RGB32F frame down to pinned memory)",
                "launches_per_call": int(ste["launches"]),
                "strategy": ("streamed rows (fused kernel, finished tile rows copied while the frame is traced)"
-                            if ste["launches"] <= 3 else "copy-engine bands") + " -- chosen by the entry's own measurement",
+                            if ste["launches"] <= 3 else "copy-engine bands") + " -- static rule of the entry (1 light slot, 1 spp -> streamed)",
                "frame_d2h_copy_alone_ms": float(np.mean(tc)) * 1e3,
                "rgb8": {"value": rays_total / (rgb8_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": rgb8_ms,
                         "d2h_bytes_per_step": int(st8["d2h_bytes"]),
                         "api": "yahr_b200_render_rgb8 (8-bit output stage on the GPU, as the yahr CLI does)"},
-               "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
+               "scene_create_ms": R.timing["scene_ms"], "exchange_setup_ms": R.timing["exchange_ms"],
+               "renderer_init_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
     else:
         # every rank renders its own tile rows through the host-buffer shard entry and copies them into ONE pinned
         # host frame shared by the ranks (POSIX shared memory): N PCIe links, no inter-GPU exchange
@@ -377,7 +538,7 @@ def run_ours(args):
         host = SharedHostFrame(w, h, rank, world, barrier=barrier)
         times = []
         ste = None
-        e2e_warmup = max(7, args.warmup)               # past the entry's six strategy-measuring calls (see above)
+        e2e_warmup = args.warmup
         for i in range(e2e_warmup + args.steps):
             flush.zero_()
             barrier()                                  # ranks leave the barrier together: a common start
@@ -392,48 +553,44 @@ def run_ours(args):
         bytes_t = torch.tensor([float(ste["h2d_bytes"]), float(ste["d2h_bytes"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(bytes_t)
         e2e_ms = float(tt.mean()) * 1e3
+        if rank == 0:
+            host_frames = {"e2e_float": host.array.copy()}
         e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(bytes_t[0]), "d2h_bytes_per_step": int(bytes_t[1]),
                "api": "yahr_b200_render_shard on every rank (tile rows r mod N == rank) into one shared pinned host frame"
                       + ("" if host.pinned else " (cudaHostRegister failed: pageable)"),
                "launches_per_call": int(ste["launches"]),
                "strategy": ("streamed rows (fused kernel, finished tile rows copied while the frame is traced)"
-                            if ste["launches"] <= 3 else "copy-engine bands") + " -- chosen by the entry's own measurement",
-               "scene_create_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
+                            if ste["launches"] <= 3 else "copy-engine bands") + " -- static rule of the entry (1 light slot, 1 spp -> streamed)",
+               "scene_create_ms": R.timing["scene_ms"], "exchange_setup_ms": R.timing["exchange_ms"],
+               "renderer_init_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
         host.close()
 
+    # ---- frame check (outside every timed region): the frame this run produced is the right one ----------------
+    frame_check = check_frames(R, sc, cam, args, trav, world, rank, barrier, host_frames)
+
+    # the GPU's own work counters (counting build of the default kernels): visited nodes, primitive tests, probes
+    gpu_counts = None
+    if args.depth == 1 and args.spp == 1 and args.kernel == 0 and not args.no_gpu_counts:
+        try:
+            gpu_counts = R.work_counts(recursion_depth=args.depth, spp=args.spp, traversal=trav)
+        except Exception as e:        # noqa: BLE001 -- a diagnostic, never fatal for the measurement
+            gpu_counts = {"error": str(e)}
+
     # ---- roofline of the dominant kernel ----------------------------------------------------
-    peak, peak_src = peaks()
-    k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
-    # the oracle's per-ray byte counts (tools/bytes_per_ray.json) are for the configured workloads at depth 1, 1 spp
-    bpr = BYTES_PER_RAY.get(args.workload) if (args.depth == 1 and args.spp == 1) else None
-    roofline = None
-    if k_ms and bpr:
-        achieved = rays_local * bpr / (k_ms * 1e-3) / 1e9
-        wf = launches_per_step > 1
-        ph = [float(x) for x in np.mean(np.asarray(phase_ms), axis=0)]
-        traffic, bound_by = ncu_figures(args.workload, "wavefront" if wf else "mega")
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic,
-                    "kernel": ("k_wf_primary (primary trace + shading, dominant) + k_wf_shadow; one frame = one launch "
-                               "of each") if wf else "k_render_mega",
-                    "kernel_ms": k_ms,
-                    "phase_ms": {"primary_trace_and_shade": ph[0], "shadow_trace": ph[2]} if wf else None,
-                    "bytes_per_ray": bpr, "rays_per_launch": rays_local, "peak_source": peak_src,
-                    # what actually bounds the kernels (from the committed ncu capture):
-                    "dram_frac_actual": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                    "bound_by": bound_by,
-                    "note": "`achieved` counts ALGORITHMIC bytes under the reference's traversal (SURVEY.md 8d): every "
-                            "box / primitive fetch of every ray at 32 B per box.  The scene is cache-resident, so `frac` "
-                            "can exceed 1 and is not an HBM-efficiency claim: real DRAM traffic is `traffic` "
-                            "(dram_frac_actual of peak).  The kernels are co-limited by instruction issue and by the "
-                            "L1 data pipe (one 128 B wavefront per cycle per SM; a 4-wide node is 112 B per ray per "
-                            "step): see bound_by and DESIGN.md section 4"}
+    roofline = build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clk.summary(), launches_per_step, world,
+                              gpu_counts)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline_run(sc, cam, target_seconds=args.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "bytes_per_ray_sample")}
+
+    R.close()
+    del R
+    extra = None
+    if not args.no_extra and args.workload == "c4-terrain":
+        extra = extra_workloads(args, world, rank, barrier)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -441,13 +598,13 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "name": args.workload, "rays_per_frame": rays_total,
                            "primary": n_primary, "shadow": n_shadow, "traversal": args.traversal,
-                           "exchange": R.mode, "l2": "flushed between timed iterations (256 MiB write)",
+                           "exchange": exchange_mode, "l2": "flushed between timed iterations (256 MiB write)",
                            "bvh_nodes": info["n_nodes"], "bvh_depth": info["depth"],
                            "scene_bytes": info["device_bytes"], "bvh_build_ms": info["build_ms"]},
                 "frames_per_s": 1e3 / ms_per_step, "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu,
+                "frame_check": frame_check, "extra_workloads": extra}
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
-    R.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -471,6 +628,10 @@ def main():
     ap.add_argument("--tune", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block (C5, 64 spp, area light)")
+    ap.add_argument("--no-gpu-counts", action="store_true", help="skip the counting-build pass")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--check-oracle", action="store_true", help="frame_check against the oracle also for spp > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its

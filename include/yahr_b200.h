@@ -183,6 +183,16 @@ int yahr_b200_render(yahr_scene* scene, const yahr_camera* cam, int recursion_de
 int yahr_b200_render_device(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
                             float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats);
 
+/* Measurement aid (no reference counterpart; not on the product path): the same frame as yahr_b200_render_device
+ * through the COUNTING build of the wavefront kernels -- identical results plus the GPU's own work counters, from
+ * which bench.py derives the bytes the kernels really request per ray (SURVEY.md 8d counts them under the reference's
+ * traversal, main.hs:73 -> Culling.hs:24-25; the 4-wide walk skips ancestor boxes).  recursion_depth 1 only.
+ * counts_out[0..7] closest-hit walks, [8..15] any-hit walks, each {4-wide node visits (128 B), binary node visits
+ * (64 B), primitive tests (48 B), normal fetches (48 B), stack pushes (8 B), stack pops (8 B), -, shaded hits}. */
+int yahr_b200_render_device_counted(yahr_scene* scene, const yahr_camera* cam, const yahr_render_opts* opts,
+                                    float* d_rgb, uint32_t* d_primid, void* stream, yahr_stats* stats,
+                                    uint64_t counts_out[16]);
+
 /* Multi-GPU device-buffer entry.  Renders the rows shard_index, shard_index + shard_count, ... of the reference's
  * tile grid into the LOCAL buffers (full-frame sized, on the scene's GPU), then pushes exactly those pixel rows into
  * the gather buffers with device-to-device copies enqueued on `stream` (the gather frame usually lives on rank 0 and

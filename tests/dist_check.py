@@ -22,10 +22,21 @@ from yahr_b200.dist import SharedHostFrame, TileShardedRenderer  # noqa: E402
 
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # YAHR_DIST_CHECK_SAME_DEVICE=1: every rank on cuda:0 (a one-GPU box).  The data plane is the same -- CUDA IPC
+    # mappings of rank 0's frame, remote stores / device-to-device pushes, the shared pinned host frame -- only the
+    # fence and the "reduce" baseline go through gloo, because NCCL refuses two ranks on one device.
+    same_device = os.environ.get("YAHR_DIST_CHECK_SAME_DEVICE") == "1"
+    if same_device:
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
+    if rank == 0:
+        print("dist_check: world=%d backend=%s devices=%d%s" % (world, dist.get_backend(), torch.cuda.device_count(),
+                                                                " (all ranks on cuda:0)" if same_device else ""), flush=True)
     for name, (sc, cam) in {"bunny": scenes.c2_bunny_proxy(960, 540, nu=80, nv=60),
                             "c1": scenes.c1_scene_yahrr(517, 389)}.items():
         w, h = api.image_size(cam)
@@ -37,6 +48,19 @@ def main():
             s.render_device(cam, full.data_ptr(), fpid.data_ptr())
             s.close()
             ref = (full, fpid)
+            # the single-GPU frame itself against the CPU oracle on every 16th tile
+            from oracle import binding as ob
+            o = ob.OracleScene(sc)
+            orgb = np.full((h, w, 3), np.nan, np.float32)
+            opid = np.full((h, w), 0xFFFFFFFE, np.uint32)
+            o.render(cam, tile_stride=16, tile_offset=3, out=(orgb, opid, np.zeros((h, w), np.float32)))
+            o.close()
+            sel = opid != 0xFFFFFFFE
+            ids_ok = np.array_equal(fpid.cpu().numpy().view(np.uint32)[sel], opid[sel])
+            err = float(np.nanmax(np.abs(full.cpu().numpy()[sel].astype(np.float64) - orgb[sel].astype(np.float64))))
+            print("%s single-GPU frame vs oracle on %d sampled pixels: ids equal=%s max abs err %.2e"
+                  % (name, int(sel.sum()), ids_ok, err), flush=True)
+            ok = ok and ids_ok and err <= 1e-3
         for mode in ("rows", "p2p", "reduce"):
             R = TileShardedRenderer(sc, cam, mode=mode, want_primid=True)
             for _ in range(3):

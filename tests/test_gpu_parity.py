@@ -476,6 +476,165 @@ def test_full_size_c5_sampled_oracle(area):
     assert (np.sqrt((d ** 2).mean(axis=0)) <= RMSE).all()
 
 
+def _sampled_oracle(sc, cam, spp, seed, stride, offset):
+    w, h = api.image_size(cam)
+    o = ob.OracleScene(sc)
+    orgb = np.full((h, w, 3), np.nan, np.float32)
+    opid = np.full((h, w), 0xFFFFFFFE, np.uint32)
+    o.render(cam, spp=spp, seed=seed, tile_stride=stride, tile_offset=offset, out=(orgb, opid, np.zeros((h, w), np.float32)))
+    o.close()
+    return orgb, opid, opid != 0xFFFFFFFE
+
+
+def _check_sampled(rgb, pid, orgb, opid, sel, what):
+    assert np.array_equal(pid[sel], opid[sel]), what + ": primitive IDs differ from the oracle"
+    a, b = rgb[sel], orgb[sel]
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), what + ": NaN pixels differ"
+    d = np.where(nan_a, 0, a).astype(np.float64) - np.where(nan_b, 0, b).astype(np.float64)
+    assert np.abs(d).max() <= MAX_ABS, "%s: max abs radiance error %g" % (what, np.abs(d).max())
+    assert (np.sqrt((d ** 2).mean(axis=0)) <= RMSE).all(), what + ": RMSE"
+
+
+def test_full_size_c2_sampled_oracle():
+    """BASELINE config C2 as named: bunny proxy (69 566 triangles), 1920x1080, 16 spp, point + area light; oracle
+    parity on every 64th tile of the full-size frame, plus the 1 spp point-light frame (the reference's own
+    configuration) through the host entry and the device entry."""
+    torch = torch_mod()
+    sc, cam = scenes.c2_bunny_proxy(area_samples=1)
+    w, h = api.image_size(cam)
+    assert (w, h) == (1920, 1080)
+    s = api.Scene(sc)
+    assert s.info()["n_primitives"] >= 69_000
+    rgb, pid, st = s.render(cam, spp=16, seed=2024)
+    assert st["n_primary"] == 16 * w * h
+    s.close()
+    orgb, opid, sel = _sampled_oracle(sc, cam, 16, 2024, 64, 11)
+    assert sel.sum() > 30000
+    _check_sampled(rgb, pid, orgb, opid, sel, "C2 16 spp area")
+    sc1, _ = scenes.c2_bunny_proxy()
+    s = api.Scene(sc1)
+    rgb, pid, _ = s.render(cam)
+    d_rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    d_pid = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr())
+    s.close()
+    assert np.array_equal(rgb.view(np.uint32), d_rgb.cpu().numpy().view(np.uint32))
+    assert np.array_equal(pid, d_pid.cpu().numpy().view(np.uint32))
+    orgb, opid, sel = _sampled_oracle(sc1, cam, 1, 0, 16, 5)
+    _check_sampled(rgb, pid, orgb, opid, sel, "C2 1 spp")
+
+
+def test_full_size_c3_sampled_oracle():
+    """BASELINE config C3 as named: 32^3 sphere grid (generalises Spec.hs:221-262), 2048x2048, 4 spp, shadow rays;
+    oracle parity on every 128th tile of the full-size frame, and at 1 spp on every 64th."""
+    sc, cam = scenes.c3_sphere_grid()
+    w, h = api.image_size(cam)
+    assert (w, h) == (2048, 2048)
+    s = api.Scene(sc)
+    assert s.info()["n_primitives"] == 32 ** 3
+    rgb4, pid4, st4 = s.render(cam, spp=4, seed=5)
+    rgb1, pid1, st1 = s.render(cam)
+    s.close()
+    assert st4["n_primary"] == 4 * w * h and st1["n_primary"] == w * h and st1["n_shadow"] > 0
+    orgb, opid, sel = _sampled_oracle(sc, cam, 4, 5, 128, 9)
+    assert sel.sum() > 20000
+    _check_sampled(rgb4, pid4, orgb, opid, sel, "C3 4 spp")
+    orgb, opid, sel = _sampled_oracle(sc, cam, 1, 0, 64, 3)
+    _check_sampled(rgb1, pid1, orgb, opid, sel, "C3 1 spp")
+
+
+def test_full_size_c4_soup_sampled_oracle():
+    """BASELINE config C4, soup half: 1 M random triangles at 3840x2160 -- the hardest case for the reference's
+    left-first order (Culling.hs:24-25: 235 box tests per ray, deep stacks).  Oracle parity on every 256th tile; the
+    wavefront set on the binary tree and on its 4-wide collapse must agree bit for bit on the whole frame."""
+    torch = torch_mod()
+    sc, cam = scenes.c4_soup()
+    w, h = api.image_size(cam)
+    assert (w, h) == (3840, 2160)
+    s = api.Scene(sc)
+    assert s.info()["n_primitives"] == 1_000_000
+    a = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    ap = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    b = torch.zeros_like(a)
+    bp = torch.zeros_like(ap)
+    st = s.render_device(cam, a.data_ptr(), ap.data_ptr())
+    s.render_device(cam, b.data_ptr(), bp.data_ptr(), kernel=2, tune=0x400)          # binary tree
+    assert torch.equal(ap, bp) and torch.equal(a.view(torch.int32), b.view(torch.int32))
+    s.render_device(cam, b.data_ptr(), bp.data_ptr(), kernel=2, tune=0x4000)         # 4-wide tree pinned
+    assert torch.equal(ap, bp) and torch.equal(a.view(torch.int32), b.view(torch.int32))
+    s.close()
+    assert st["n_primary"] == w * h
+    orgb, opid, sel = _sampled_oracle(sc, cam, 1, 0, 256, 17)
+    assert sel.sum() > 20000
+    _check_sampled(a.cpu().numpy(), ap.cpu().numpy().view(np.uint32), orgb, opid, sel, "C4 soup")
+
+
+def test_full_size_c4_terrain_host_entries(monkeypatch):
+    """C4 terrain at 3840x2160 through every host-buffer path: streamed rows and copy-engine bands, each with the
+    primitive-ID plane, and the 8-bit entry (streamed and banded) -- all against the device-resident frame."""
+    torch = torch_mod()
+    sc, cam = scenes.c4_terrain()
+    w, h = api.image_size(cam)
+    s = api.Scene(sc)
+    dev = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    dpid = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    s.render_device(cam, dev.data_ptr(), dpid.data_ptr())
+    ref = dev.cpu().numpy()
+    rpid = dpid.cpu().numpy().view(np.uint32)
+    ref8 = api.quantize_rgb8_host(ref)
+    for stream in ("1", "0"):
+        monkeypatch.setenv("YAHR_B200_HOST_STREAM", stream)
+        monkeypatch.setenv("YAHR_B200_POISON_FRAME", "1")
+        rgb, pid, st = s.render(cam)
+        assert np.array_equal(rgb.view(np.uint32), ref.view(np.uint32)), "float frame, stream=" + stream
+        assert np.array_equal(pid, rpid), "primid plane, stream=" + stream
+        assert st["d2h_bytes"] == w * h * 16
+        rgb8, st8 = s.render_rgb8(cam)
+        assert np.array_equal(rgb8, ref8), "8-bit frame, stream=" + stream
+        assert st8["d2h_bytes"] == w * h * 3
+    monkeypatch.delenv("YAHR_B200_HOST_STREAM")
+    rgb8, st8 = s.render_rgb8(cam)                      # the static rule: first call of this kind, streamed
+    assert np.array_equal(rgb8, ref8) and st8["launches"] <= 3
+    s.close()
+
+
+def test_spp_scratch_regrows_for_a_larger_image(monkeypatch):
+    """One scene handle, a small image with many samples per launch, then a larger image with fewer: the accumulator
+    must grow with the image even when the per-sample scratch of the first call is still large enough."""
+    sc, _ = scenes.c1_scene_yahrr()
+    small = scenes._camera(200, 150, 1.5, [0.4, -0.3, 1], [0, 1, 0], [-4, 3, 2])
+    large = scenes._camera(300, 200, 1.5, [0.4, -0.3, 1], [0, 1, 0], [-4, 3, 2])
+    s = api.Scene(sc)
+    monkeypatch.setenv("YAHR_B200_SAMPLES_PER_LAUNCH", "4")
+    s.render(small, spp=4, seed=3)
+    monkeypatch.setenv("YAHR_B200_SAMPLES_PER_LAUNCH", "1")
+    rgb, pid, _ = s.render(large, spp=4, seed=3)
+    s.close()
+    fresh = api.Scene(sc)
+    rgb2, pid2, _ = fresh.render(large, spp=4, seed=3)
+    fresh.close()
+    assert np.array_equal(rgb.view(np.uint32), rgb2.view(np.uint32)) and np.array_equal(pid, pid2)
+    o = ob.OracleScene(sc)
+    orgb, opid, _, _ = o.render(large, spp=4, seed=3)
+    o.close()
+    compare(rgb, pid, orgb, opid, 1.0, "small-then-large spp")
+
+
+def test_out_buffers_are_validated():
+    sc, cam = scenes.c1_scene_yahrr(64, 48)
+    s = api.Scene(sc)
+    with pytest.raises(ValueError):
+        s.render(cam, out=(np.zeros((48, 64, 3), np.float64), None))
+    with pytest.raises(ValueError):
+        s.render(cam, out=(np.zeros((64, 48, 3), np.float32), None))
+    with pytest.raises(ValueError):
+        s.render(cam, out=(np.zeros((48, 128, 3), np.float32)[:, ::2], None))
+    with pytest.raises(ValueError):
+        s.render_rgb8(cam, out=np.zeros((48, 64, 3), np.float32))
+    s.close()
+
+
 def test_empty_scene_renders_black():
     sc = scenes._empty_scene()
     cam = scenes._camera(64, 48, 1.0, [0, 0, 1], [0, 1, 0], [0, 0, 0])

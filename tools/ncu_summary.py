@@ -6,8 +6,12 @@ writes <out>.txt and <out>.json.  Needs `ncu` on PATH (no GPU)."""
 import csv
 import io
 import json
+import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from yahr_b200.api import source_fingerprint  # noqa: E402
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -29,6 +33,8 @@ METRICS = [
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
     "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "sass__inst_executed_local_loads",
     "sass__inst_executed_local_stores",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_active.avg",
+    "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
 ]
 
 
@@ -59,7 +65,8 @@ def main():
         scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
         return None if v is None else v * scale
 
-    js = {"source": out + ".txt", "kernels": []}
+    # the capture describes the kernels of THIS source tree: bench.py refuses it when the sources have changed since
+    js = {"source": out + ".txt", "fingerprint": source_fingerprint(), "kernels": []}
     for d in data:
         js["kernels"].append({
             "name": d[col["Kernel Name"]],
@@ -71,6 +78,12 @@ def main():
             "l1_hit": f(d, "l1tex__t_sector_hit_rate.pct"), "l2_hit": f(d, "lts__t_sector_hit_rate.pct"),
             "l1_lsu_wavefronts_pct": f(d, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
             "warps_active_pct": f(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "inst_executed": f(d, "smsp__inst_executed.sum"),
+            "l1_lsu_wavefronts": f(d, "l1tex__data_pipe_lsu_wavefronts.sum"),
+            "grid": f(d, "launch__grid_size"), "registers": f(d, "launch__registers_per_thread"),
+            "local_sectors": (f(d, "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum") or 0)
+            + (f(d, "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum") or 0),
+            "global_ld_sectors": f(d, "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
         })
     json.dump(js, open(out + ".json", "w"), indent=1)
     print("\n".join(lines))

@@ -82,7 +82,7 @@ def build_library(force=False):
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "yahr_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
-        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -211,6 +211,29 @@ def image_size(cam):
     return int(np.floor(c.imW)), int(np.floor(c.imH))
 
 
+def source_fingerprint():
+    """sha256 over the sources libyahr_b200.so is built from (csrc/*, include/yahr_b200.h).  Profiles written by
+    tools/ncu_summary.py carry it, and bench.py only trusts a capture whose fingerprint is the current tree's."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".cpp")) or f == "Makefile")
+    for f in files:
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(os.path.dirname(_HERE), "include", "yahr_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def _check_out(a, shape, dtype, what):
+    """The C ABI writes shape-many elements of dtype through a raw pointer: refuse anything that is not exactly that."""
+    if not isinstance(a, np.ndarray):
+        raise ValueError("%s must be a numpy array" % what)
+    if a.dtype != np.dtype(dtype) or tuple(a.shape) != tuple(shape) or not a.flags.c_contiguous or not a.flags.writeable:
+        raise ValueError("%s must be a writeable C-contiguous %s array of shape %s (got %s %s%s)"
+                         % (what, np.dtype(dtype).name, tuple(shape), a.dtype.name, tuple(a.shape),
+                            "" if a.flags.c_contiguous else ", not contiguous"))
+
+
 def device_count():
     return lib().yahr_b200_device_count()
 
@@ -251,6 +274,9 @@ class Scene:
             pid = np.empty((h, w), np.uint32) if want_primid else None
         else:
             rgb, pid = out
+            _check_out(rgb, (h, w, 3), np.float32, "out[0] (rgb)")
+            if pid is not None:
+                _check_out(pid, (h, w), np.uint32, "out[1] (primid)")
         st = Stats()
         _check(lib().yahr_b200_render(self._h, C.byref(c), recursion_depth, spp, seed, rgb.ctypes.data,
                                       pid.ctypes.data if pid is not None else None, C.byref(st)))
@@ -261,6 +287,11 @@ class Scene:
         full-frame host buffers out = (rgb [H,W,3] float32, primid [H,W] uint32 or None)."""
         c = make_camera(cam)
         rgb, pid = out
+        w, h = int(np.floor(c.imW)), int(np.floor(c.imH))
+        if hasattr(rgb, "ctypes"):
+            _check_out(rgb, (h, w, 3), np.float32, "out[0] (rgb)")
+        if pid is not None and hasattr(pid, "ctypes"):
+            _check_out(pid, (h, w), np.uint32, "out[1] (primid)")
         st = Stats()
         L = lib()
         L.yahr_b200_render_shard.restype = C.c_int
@@ -302,6 +333,7 @@ class Scene:
         c = make_camera(cam)
         w, h = int(np.floor(c.imW)), int(np.floor(c.imH))
         rgb8 = np.empty((h, w, 3), np.uint8) if out is None else out
+        _check_out(rgb8, (h, w, 3), np.uint8, "out (rgb8)")
         L = lib()
         L.yahr_b200_render_rgb8.restype = C.c_int
         L.yahr_b200_render_rgb8.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_uint64, C.c_void_p,
@@ -331,6 +363,50 @@ class Scene:
 
 def _ptr(x):
     return C.c_void_p(x) if x else None
+
+
+def _render_device_counted(self, cam, d_rgb, d_primid=None, recursion_depth=1, spp=1, seed=0,
+                           traversal=TRAVERSAL_REFERENCE, tile_stride=1, tile_offset=0, stream=None, kernel=0, tune=0,
+                           by_rows=False):
+    """yahr_b200_render_device_counted: the frame through the counting build of the wavefront kernels.  Returns a
+    dict of the GPU's own work counters and the bytes the kernels request per ray (measurement aid)."""
+    c = make_camera(cam)
+    o = RenderOpts()
+    o.recursion_depth, o.spp, o.seed = recursion_depth, spp, seed
+    o.traversal, o.tile_stride, o.tile_offset, o.kernel = traversal, tile_stride, tile_offset, kernel
+    o.reserved[0] = tune
+    o.reserved[1] = 1 if by_rows else 0
+    st = Stats()
+    counts = (C.c_uint64 * 16)()
+    L = lib()
+    L.yahr_b200_render_device_counted.restype = C.c_int
+    L.yahr_b200_render_device_counted.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderOpts), C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.POINTER(Stats), C.POINTER(C.c_uint64)]
+    _check(L.yahr_b200_render_device_counted(self._h, C.byref(c), C.byref(o), C.c_void_p(d_rgb), _ptr(d_primid),
+                                             _ptr(stream), C.byref(st), counts))
+    names = ("wide_nodes", "binary_nodes", "prim_tests", "normal_fetches", "stack_pushes", "stack_pops", "_", "shaded")
+    out = {"closest_hit": {n: int(counts[k]) for k, n in enumerate(names) if n != "_"},
+           "any_hit": {n: int(counts[8 + k]) for k, n in enumerate(names) if n not in ("_", "shaded")}}
+    s_ = st.as_dict()
+    rays = s_["n_primary"] + s_["n_shadow"] + s_["n_secondary"]
+    tot = {n: out["closest_hit"].get(n, 0) + out["any_hit"].get(n, 0) for n in names if n != "_"}
+    # bytes the kernels REQUEST (from L1/L2/HBM, whatever serves them): 128 B per 4-wide node, 64 B per binary node, 48 B
+    # per primitive test, 48 B per normal fetch, 8 B per stack push / pop; per shaded hit the surface (48 + 48 B),
+    # material (32 B) and light (32 B); per probe its queue record written and read; per primary ray the pixel-table
+    # entry (4 B) and the pixel (12 B)
+    probe_bytes = 2 * 32 if s_["launches"] <= 3 else 2 * 48
+    b = (128 * tot["wide_nodes"] + 64 * tot["binary_nodes"] + 48 * tot["prim_tests"] + 48 * tot["normal_fetches"]
+         + 8 * (tot["stack_pushes"] + tot["stack_pops"]) + 160 * tot["shaded"] + probe_bytes * s_["n_shadow"]
+         + 16 * s_["n_primary"])
+    out.update({"rays": int(rays), "n_primary": int(s_["n_primary"]), "n_shadow": int(s_["n_shadow"]),
+                "bytes_requested": int(b), "bytes_per_ray_gpu": b / max(rays, 1),
+                "wide_nodes_per_ray": tot["wide_nodes"] / max(rays, 1), "prim_tests_per_ray": tot["prim_tests"] / max(rays, 1),
+                "stack_bytes_share": 8 * (tot["stack_pushes"] + tot["stack_pops"]) / max(b, 1),
+                "probe_record_bytes": probe_bytes // 2})
+    return out
+
+
+Scene.render_device_counted = _render_device_counted
 
 
 def render_device_shard(scene, cam, shard_index, shard_count, d_rgb_local, d_rgb_gather=None, d_primid_local=None,

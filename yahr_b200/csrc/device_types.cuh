@@ -93,7 +93,8 @@ struct WavefrontParams {
   float4* q2;                 //                (contribution.rgb, -)
   unsigned char* visibility;  // dense mode: per slot 1 = unoccluded
   uint32_t* bandStat;         // host-buffer entry: += shadow probes of this launch (cost of the band, for scheduling) or NULL
-  uint32_t* work;             // [0] primary work counter, [1] shadow work counter, [2] queue length, [3] probes
+  uint32_t* work;             // [0] primary work counter, [1] shadow work counter / chunks claimed, [2] queue length,
+                              // [3] probes, [4] secondary rays, [5] k_wf_persist: primary batches whose probes are committed
   float* sampleOut;           // where this pass writes its radiance (the frame, or sampleBuf for spp > 1)
   float* sampleBuf;           // W*H*3 scratch (spp > 1)
   float* accum;               // W*H*3 running sum (spp > 1)
@@ -105,6 +106,14 @@ struct WavefrontParams {
   uint32_t* rowDone;              // finalised pixels per tile row (zeroed before the launch)
   volatile uint32_t* rowFlags;    // mapped host memory: rowFlags[row] = rowSeq once the row is complete in device memory
   uint32_t rowSeq;
+  // k_wf_persist (one launch per frame): probes are appended to q0 / q2 (32 B each) and consumed in committed chunks of 32
+  uint32_t persist;               // 1: one light slot, depth 1, 4-wide tree -> k_wf_persist instead of primary + shadow
+  uint32_t* commit;               // per chunk of 32 queue entries: entries written so far (all zero between launches)
+  uint32_t stackShared;           // traversal-stack entries per lane kept in shared memory (0, 8 or 12)
+  uint32_t discardQueue;          // consumed queue lines are dropped from L2 without write-back (discard.global.L2)
+  unsigned long long* workStats;  // counting build only: 2 x 8 work counters (closest-hit walks, any-hit walks); else NULL
+  unsigned char* rgb8;            // 8-bit host-buffer entry through the streamed rows: the per-batch kernels store the
+                                  // quantised pixel (main.hs:142) here INSTEAD of the float frame; NULL otherwise
 };
 
 }  // namespace yb

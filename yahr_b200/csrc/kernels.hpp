@@ -20,4 +20,9 @@ namespace yb {
 cudaError_t launchPixelTable(WavefrontParams W, uint32_t* table, cudaStream_t stream);
 cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
                             cudaEvent_t* phaseEvents);
+// The counting build of the same kernels (wavefront_count.cu): depth 1 only; fills W.workStats.
+namespace counted {
+cudaError_t launchWavefrontCounted(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
+                                   cudaEvent_t* phaseEvents);
+}
 }  // namespace yb

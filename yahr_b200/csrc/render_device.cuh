@@ -77,7 +77,7 @@ __device__ __forceinline__ bool boxTest(float lox, float loy, float loz, float h
 // collideTriangle / collideSphere acceptance (Shapes.hs:13-29, 36-59) for the primitive at DFS
 // position idx.  Returns true and t iff the reference returns `Just`.
 __device__ __forceinline__ bool hitPrimitive(const DeviceScene& sc, uint32_t idx, const Ray& r, float tMax,
-                                             float& tOut) {
+                                             float& tOut, uint32_t* candidates = nullptr) {
   const float4 A = __ldg(&sc.prims[3 * (size_t)idx + 0]);
   const float4 B = __ldg(&sc.prims[3 * (size_t)idx + 1]);
   if (__float_as_uint(A.w) & 1u) {
@@ -94,6 +94,7 @@ __device__ __forceinline__ bool hitPrimitive(const DeviceScene& sc, uint32_t idx
     if (!(b0 >= 0.0f && b0 <= 1.0f && b1 >= 0.0f && b1 <= 1.0f && b2 >= 0.0f && b2 <= 1.0f && t > 0.0f &&
           t <= tMax))
       return false;
+    if (candidates) ++*candidates;                    // counting build: the normals are fetched for this test
     const V3 n0 = xyz(__ldg(&sc.normals[3 * (size_t)idx + 0]));
     const V3 n1 = xyz(__ldg(&sc.normals[3 * (size_t)idx + 1]));
     const V3 n2 = xyz(__ldg(&sc.normals[3 * (size_t)idx + 2]));

@@ -24,25 +24,75 @@
 #include "kernels.hpp"
 #include "render_device.cuh"
 
-namespace yb {
+// This file is compiled twice: as it stands (the production kernels), and through wavefront_count.cu with
+// YB_COUNT_WORK defined -- the COUNTING build: the same kernels in namespace yb::counted with per-lane work counters
+// (visited nodes, primitive tests, normal fetches, stack pushes / pops, shaded hits, probes) summed into
+// WavefrontParams::workStats.  The production kernels contain no trace of the counters.
+#ifdef YB_COUNT_WORK
+#define YB_WF_OPEN namespace yb { namespace counted {
+#define YB_WF_CLOSE } }
+#define YB_CNT(s, k) (++(s).cnt[k])
+#define YB_CNT_INIT(s) do { for (int k_ = 0; k_ < kNumCnt; ++k_) (s).cnt[k_] = 0u; } while (0)
+#else
+#define YB_WF_OPEN namespace yb {
+#define YB_WF_CLOSE }
+#define YB_CNT(s, k) ((void)0)
+#define YB_CNT_INIT(s) ((void)0)
+#endif
+
+YB_WF_OPEN
 
 using namespace dev;
 
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kStackEntries = 64;
+
+// per-lane work counters of the counting build (indices into Trav::cnt and, per walk kind, WavefrontParams::workStats)
+enum { kCntWide = 0, kCntBinary, kCntPrim, kCntCand, kCntPush, kCntPop, kNumCnt };
 
 struct Trav {
   uint32_t cur;
   int sp;
   float tMax;
   uint32_t best;
+#ifdef YB_COUNT_WORK
+  uint32_t cnt[kNumCnt];
+#endif
 };
 
+// Traversal stack of a lane: (subtree reference, entry distance) pairs.  The first SH entries live in SHARED memory,
+// entry i of thread t at column t of row i (row = 128 x 8 B): whatever the lanes' stack pointers are, lane l always
+// hits banks 2l, 2l+1 -- every push / pop is conflict-free (two 128 B wavefronts per warp) and stays out of the L1
+// tag stage and of the L1 lines the tree lives in.  Deeper entries (rare) spill to local memory.  SH = 0: the whole
+// stack in local memory (round 1: 35 % of k_wf_primary's L1 sectors were stack traffic, profiles/r1r).
+template <int SH>
+struct Stack {
+  uint2* sh;
+  uint2* lo;
+  __device__ __forceinline__ void store(int i, uint2 e) const {
+    if (SH == 0) lo[i] = e;
+    else if (i < SH) sh[i * 128] = e;
+    else lo[i - SH] = e;
+  }
+  __device__ __forceinline__ uint2 load(int i) const {
+    if (SH == 0) return lo[i];
+    if (i < SH) return sh[i * 128];
+    return lo[i - SH];
+  }
+};
+#define YB_STACK(SH)                                                     \
+  __shared__ uint2 shStack_[(SH) > 0 ? (SH) * 128 : 1];                  \
+  uint2 loStack_[kStackEntries - (SH)];                                  \
+  const Stack<(SH)> stack{shStack_ + threadIdx.x, loStack_}
+
 // Pops the next deferred subtree whose box test still passes with the current tMax.
-__device__ __forceinline__ bool popNext(Trav& s, const uint2* stack) {
+template <class STK>
+__device__ __forceinline__ bool popNext(Trav& s, const STK& stack) {
   while (s.sp > 0) {
-    const uint2 e = stack[--s.sp];
+    const uint2 e = stack.load(--s.sp);
+    YB_CNT(s, kCntPop);
     if (__uint_as_float(e.y) <= s.tMax) { s.cur = e.x; return true; }
   }
   return false;
@@ -101,9 +151,10 @@ __device__ __forceinline__ void childTestsOct(const float4& n0, const float4& n1
 // One inner-node visit.  OCT in 0..7: every busy lane of the warp has that octant (packed fast path);
 // OCT = -1: generic path (mixed octants, or some ray whose slab products can be NaN).
 // Returns false when the walk is finished (nothing left to visit).
-template <bool ORDERED, int OCT>
+template <bool ORDERED, int OCT, class STK>
 __device__ __forceinline__ bool innerStep(const DeviceScene& sc, const Ray& r, const RayPack& rp, Trav& s,
-                                          uint2* stack) {
+                                          const STK& stack) {
+  YB_CNT(s, kCntBinary);
   const float4* np = sc.nodes + 4 * (size_t)s.cur;
   const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
   float keyL, keyR;
@@ -118,11 +169,12 @@ __device__ __forceinline__ bool innerStep(const DeviceScene& sc, const Ray& r, c
   passL = passL && refL != kDevRefNull;
   passR = passR && refR != kDevRefNull;
   if (passL && passR) {
+    YB_CNT(s, kCntPush);
     if (ORDERED && keyR < keyL) {
-      stack[s.sp++] = make_uint2(refL, __float_as_uint(keyL));
+      stack.store(s.sp++, make_uint2(refL, __float_as_uint(keyL)));
       s.cur = refR;
     } else {
-      stack[s.sp++] = make_uint2(refR, __float_as_uint(keyR));
+      stack.store(s.sp++, make_uint2(refR, __float_as_uint(keyR)));
       s.cur = refL;
     }
     return true;
@@ -134,8 +186,8 @@ __device__ __forceinline__ bool innerStep(const DeviceScene& sc, const Ray& r, c
 
 // One leaf visit (collideAll over the leaf's primitives in order).  Returns false when finished.
 // anyRt: any-hit decided at run time (k_wf_fused shares ONE copy of the walk between its closest-hit and any-hit phases).
-template <bool ANY_HIT, bool ORDERED>
-__device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool anyRt = false) {
+template <bool ANY_HIT, bool ORDERED, class STK>
+__device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool anyRt = false) {
   uint32_t first, count;
   if ((s.cur & kDevRefMultiBits) == kDevRefMultiBits) {
     const uint2 ml = __ldg(&sc.multiLeaves[s.cur & 0x3FFFFFFFu]);
@@ -146,7 +198,12 @@ __device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Tr
   for (uint32_t k = 0; k < count; ++k) {
     const uint32_t idx = first + k;
     float t;
+    YB_CNT(s, kCntPrim);
+#ifdef YB_COUNT_WORK
+    if (hitPrimitive(sc, idx, r, s.tMax, t, &s.cnt[kCntCand])) {
+#else
     if (hitPrimitive(sc, idx, r, s.tMax, t)) {
+#endif
       if (!ORDERED || t < s.tMax || s.best == kNoHit || idx > s.best) {
         s.best = idx; s.tMax = t;
         if (ANY_HIT || anyRt) return false;
@@ -157,8 +214,8 @@ __device__ __forceinline__ bool leafStep(const DeviceScene& sc, const Ray& r, Tr
 }
 
 // Runs the walks of a whole warp to completion with leaf parking.  `busy` per lane.
-template <bool ANY_HIT, bool ORDERED, int OCT>
-__device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+template <bool ANY_HIT, bool ORDERED, int OCT, class STK>
+__device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool busy,
                                              int leafThreshold, bool anyRt = false) {
   const RayPack rp = packRay(r);
   for (;;) {
@@ -176,8 +233,8 @@ __device__ __forceinline__ void traverseWarpOct(const DeviceScene& sc, const Ray
 
 // Picks the octant-specialised walk when every busy lane of the warp shares one octant and no lane
 // can produce NaN slab products; otherwise the generic walk.
-template <bool ANY_HIT, bool ORDERED>
-__device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+template <bool ANY_HIT, bool ORDERED, class STK>
+__device__ __forceinline__ void traverseWarp(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool busy,
                                              int leafThreshold, bool packed) {
   const unsigned mBusy = __ballot_sync(kFull, busy);
   if (mBusy == 0) return;
@@ -228,8 +285,9 @@ __device__ __forceinline__ void wideChildTest(const float4& b, float zlo, float 
 // One wide-node visit: four child box tests; the first passing child (left-first order) is entered, the
 // later passing ones are pushed in reverse order with their entry distance (re-validated against the then
 // current tMax when popped, exactly like the binary walk).  Returns false when the walk is finished.
-template <int OCT>
-__device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& rp, Trav& s, uint2* stack) {
+template <int OCT, class STK>
+__device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& rp, Trav& s, const STK& stack) {
+  YB_CNT(s, kCntWide);
   const float4* np = sc.wide + kWideNodeVec * (size_t)s.cur;
   const float4 b0 = __ldg(np + 0), b1 = __ldg(np + 1), b2 = __ldg(np + 2), b3 = __ldg(np + 3);
   const float4 z01 = __ldg(np + 4), z23 = __ldg(np + 5), rf = __ldg(np + 6);
@@ -248,12 +306,15 @@ __device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& r
   // are unconditional (one slot past the top is scratch), only the stack pointer moves conditionally
   int sp = s.sp;
   const bool e3 = p3 && (p0 || p1 || p2), e2 = p2 && (p0 || p1), e1 = p1 && p0;
-  if (e3) stack[sp] = make_uint2(r3, __float_as_uint(k3));
+  if (e3) stack.store(sp, make_uint2(r3, __float_as_uint(k3)));
   sp += e3 ? 1 : 0;
-  if (e2) stack[sp] = make_uint2(r2, __float_as_uint(k2));
+  if (e2) stack.store(sp, make_uint2(r2, __float_as_uint(k2)));
   sp += e2 ? 1 : 0;
-  if (e1) stack[sp] = make_uint2(r1, __float_as_uint(k1));
+  if (e1) stack.store(sp, make_uint2(r1, __float_as_uint(k1)));
   sp += e1 ? 1 : 0;
+#ifdef YB_COUNT_WORK
+  s.cnt[kCntPush] += (uint32_t)(sp - s.sp);
+#endif
   s.sp = sp;
   if (p0 || p1 || p2 || p3) {
     s.cur = p0 ? r0 : (p1 ? r1 : (p2 ? r2 : r3));
@@ -264,8 +325,8 @@ __device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& r
 
 // Inner phase of the wide walk: wide-node steps until no lane has inner work or enough lanes hold a leaf.
 // Only this loop is specialised per octant; the leaf code exists once (traverseWarpWide).
-template <int OCT>
-__device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& rp, Trav& s, uint2* stack, bool& run,
+template <int OCT, class STK>
+__device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& rp, Trav& s, const STK& stack, bool& run,
                                           int leafThreshold) {
   for (;;) {
     const bool atLeaf = run && (s.cur & kDevRefLeafBit);
@@ -276,8 +337,8 @@ __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& 
   }
 }
 
-template <bool ANY_HIT>
-__device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, uint2* stack, bool busy,
+template <bool ANY_HIT, class STK>
+__device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool busy,
                                                  int leafThreshold, bool leafRun, bool anyRt = false) {
   const bool nanLane = busy && r.exactNaN;
   bool run = busy && !r.exactNaN;
@@ -310,6 +371,22 @@ __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ra
     }
   }
   if (__any_sync(kFull, nanLane)) traverseWarpOct<ANY_HIT, false, -1>(sc, r, s, stack, nanLane, 1, anyRt);
+}
+
+// Counting build: adds this batch's per-lane counters to workStats[kind * 8 + k] (kind 0 = closest-hit walks, 1 = any-hit
+// walks); slot 6 of a kind counts the walks themselves, slot 7 the shaded hits.  No-op in the production build.
+__device__ __forceinline__ void flushCounts(const WavefrontParams& W, Trav& s, int kind, bool shaded) {
+#ifdef YB_COUNT_WORK
+  if (!W.workStats) return;
+  const unsigned lane = threadIdx.x & 31u;
+  for (int k = 0; k < kNumCnt; ++k) {
+    const uint32_t v = __reduce_add_sync(kFull, s.cnt[k]);
+    if (lane == 0 && v) atomicAdd(&W.workStats[kind * 8 + k], (unsigned long long)v);
+    s.cnt[k] = 0u;
+  }
+  const uint32_t sh = __reduce_add_sync(kFull, shaded ? 1u : 0u);
+  if (lane == 0 && sh) atomicAdd(&W.workStats[kind * 8 + 7], (unsigned long long)sh);
+#endif
 }
 
 // item index (tile-major) -> tile.  Tiles are almost uniform in size, so a proportional guess is
@@ -375,6 +452,25 @@ __device__ __forceinline__ void rowsSignal(const WavefrontParams& W, uint32_t ro
   }
 }
 
+// JuicyPixels' ImageRGBF -> 8-bit conversion of savePngImage (main.hs:142), as k_quantize_rgb8 (kernels.cu).
+__device__ __forceinline__ unsigned char quantize8(float x) {
+  const float m = (1.0f <= x) ? 1.0f : x;
+  const float c = (0.0f <= m) ? m : 0.0f;
+  return (unsigned char)(int)(255.0f * c);
+}
+
+// Final value of a pixel from one of the per-batch kernels (every pixel is stored exactly once): the float frame, or
+// -- 8-bit host-buffer entry -- the quantised bytes only.
+__device__ __forceinline__ void storeFinal(const WavefrontParams& W, size_t index, float x, float y, float z) {
+  if (W.rgb8) {
+    unsigned char* o = W.rgb8 + 3 * index;
+    o[0] = quantize8(x); o[1] = quantize8(y); o[2] = quantize8(z);
+  } else {
+    float* o = W.sampleOut + 3 * index;
+    o[0] = x; o[1] = y; o[2] = z;
+  }
+}
+
 // The shadow probe of a lane, kept in registers by the fused kernel (k_wf_fused) instead of the queue.
 struct LocalProbe {
   V3 origin, dir, contrib;
@@ -403,7 +499,8 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     float* out = W.sampleOut + 3 * (size_t)outIndex;
     const bool firstSample = W.sample + sLocal == 0u;
     if (!hit) {
-      out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;              // Nothing -> Vec3 0 0 0
+      if (FUSED) storeFinal(W, outIndex, 0.0f, 0.0f, 0.0f);
+      else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; }     // Nothing -> Vec3 0 0 0
       if (W.base.primid && firstSample) W.base.primid[pixel] = kNoHit;
     } else {
       surf = surfaceAt(sc, idx, r, tHit);
@@ -485,10 +582,10 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
   }
   if (hit && !W.dense && nEmit == 0u) {
     const float qnan = __uint_as_float(0x7FFFFFFFu);
-    float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
-    out[0] = (nanBits & 1u) ? qnan : 0.0f;
-    out[1] = (nanBits & 2u) ? qnan : 0.0f;
-    out[2] = (nanBits & 4u) ? qnan : 0.0f;
+    const size_t index = (size_t)(sLocal * W.framePixels + pixel);
+    const float x = (nanBits & 1u) ? qnan : 0.0f, y = (nanBits & 2u) ? qnan : 0.0f, z = (nanBits & 4u) ? qnan : 0.0f;
+    if (FUSED) storeFinal(W, index, x, y, z);
+    else { float* out = W.sampleOut + 3 * index; out[0] = x; out[1] = y; out[2] = z; }
   }
   if (FUSED) { local->nanBits = nanBits; local->row = row; }
   else if (W.rowFlags) rowsSignal(W, row, valid && nEmit == 0u, lane);     // pixels that are final without a shadow probe
@@ -517,9 +614,9 @@ __device__ __forceinline__ uint32_t shadowResult(const WavefrontParams& W, uint3
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, int MIN_BLOCKS, bool WIDE, bool AREA>
+template <bool ORDERED, int MIN_BLOCKS, bool WIDE, bool AREA, int SH>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
+  YB_STACK(SH);
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     uint32_t base = 0;
@@ -534,6 +631,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     Ray r;
     Trav s;
     s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    YB_CNT_INIT(s);
     bool busy = false;
     if (valid) {
       itemPixel(W, item, u, v);
@@ -544,10 +642,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     }
     if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    flushCounts(W, s, 0, valid && s.best != kNoHit);
     shadeAndEmit<AREA, false>(W, valid, item, (uint32_t)(W.base.width * v + u), v, r, s.tMax, s.best, lane, sLocal);
   }
 }
 
+#ifndef YB_COUNT_WORK
 // ---------------------------------------------------------------------------------------------
 // Fused variant for ONE light slot (the reference's configuration: one point light): the warp that traced and shaded
 // a batch walks the shadow probes of that batch itself, straight from registers -- no probe queue, no second kernel,
@@ -559,7 +659,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
 // per warp, in shared memory or in global memory around L1) was measured slower still (profiles/r1ab).
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
+  YB_STACK(0);
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     uint32_t base = 0;
@@ -601,16 +701,178 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_const
       } else if (pr.emit) {
         const bool unoccluded = s.best == kNoHit;
         const float qnan = __uint_as_float(0x7FFFFFFFu);
-        float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
-        out[0] = (pr.nanBits & 1u) ? qnan : 0.0f + (unoccluded ? pr.contrib.x : 0.0f);
-        out[1] = (pr.nanBits & 2u) ? qnan : 0.0f + (unoccluded ? pr.contrib.y : 0.0f);
-        out[2] = (pr.nanBits & 4u) ? qnan : 0.0f + (unoccluded ? pr.contrib.z : 0.0f);
+        storeFinal(W, (size_t)(sLocal * W.framePixels + pixel),
+                   (pr.nanBits & 1u) ? qnan : 0.0f + (unoccluded ? pr.contrib.x : 0.0f),
+                   (pr.nanBits & 2u) ? qnan : 0.0f + (unoccluded ? pr.contrib.y : 0.0f),
+                   (pr.nanBits & 4u) ? qnan : 0.0f + (unoccluded ? pr.contrib.z : 0.0f));
       }
     }
     if (W.rowFlags) rowsSignal(W, pr.row, valid, lane);
   }
 }
 
+#endif   // !YB_COUNT_WORK
+
+// ---------------------------------------------------------------------------------------------
+// ONE persistent kernel per frame for one light slot (the reference's configuration), with COMMITTED PROBE CHUNKS.
+// Every warp loops: (1) if a full chunk of 32 shadow probes is committed in the queue, claim it and run the any-hit
+// walks (reachable, Rays.hs:49-54) of those 32 probes -- compacted across batches, like k_wf_shadow; (2) else take a
+// batch of 32 primary items: camera rays, closest-hit walk, shading (as k_wf_primary), append the probes of the batch
+// to the queue (one atomic per warp) and COMMIT them: a release-add of the number of entries written to the counter of
+// each chunk the append touched.  A chunk is claimed only once its counter says it is complete, so nobody ever waits
+// for a producer; the last, partial chunk becomes claimable when every primary batch has committed (work[5]).
+//   * one launch: one ramp-up and one tail per frame, and the tail of the primary trace (the long horizon rays)
+//     overlaps the any-hit walks of the rest -- what a 1/N share of a frame on N GPUs needs most;
+//   * a probe is consumed microseconds after it was written: the queue lives in L2 (32 B per probe: origin + pixel,
+//     contribution + flags; direction and length are recomputed from the light), and the consumed lines are
+//     discarded from L2 so they are never written back to HBM;
+//   * pixels become final soon after their batch, roughly in item order: the streamed host rows work as with k_wf_fused;
+//   * both walks go through ONE copy of the traversal code (any-hit is a run-time flag), as in k_wf_fused.
+// Memory ordering: producers store their entries, __syncwarp, then the leader's atom.release.gpu on the chunk counter
+// (MEMBAR.ALL.GPU + RED, no L1 invalidation); a consumer's leader reads the counter with a relaxed strong load, claims
+// with a CAS, and the warp then reads the entries with ld.cg (L2) -- issued after the observation by control
+// dependence and the warp barrier.  (ld.acquire would add CCTL.IVALL: the whole L1, tree included, per claim.)
+__device__ __forceinline__ uint32_t ldRelaxed(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void addRelease(uint32_t* p, uint32_t n) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(n) : "memory");
+}
+
+template <int MIN_BLOCKS, int SH>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_constant__ WavefrontParams W) {
+  YB_STACK(SH);
+  const DeviceScene& sc = W.base.sc;
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t nWork = W.itemsPadded * W.samplesPerLaunch;
+  const uint32_t nBatches = nWork / 32u;
+  constexpr uint32_t kNone = 0xFFFFFFFFu;
+  bool primaryLeft = true;
+  uint32_t idle = 0;
+  for (;;) {
+    // ---- what this warp does next --------------------------------------------------------------------------------
+    uint32_t chunk = kNone, count = 0, base = kNone;
+    if (lane == 0) {
+      for (;;) {                                                   // (1) a committed chunk?
+        const uint32_t h = ldRelaxed(&W.work[1]);
+        const uint32_t c = ldRelaxed(&W.commit[h]);
+        uint32_t n = 0;
+        if (c == 32u) n = 32u;
+        else if (ldRelaxed(&W.work[5]) == nBatches) {              // every batch has committed: the queue length is final
+          const uint32_t t = ldRelaxed(&W.work[2]);
+          if (32u * h < t) { n = t - 32u * h < 32u ? t - 32u * h : 32u; if (ldRelaxed(&W.commit[h]) != n) n = 0; }
+        }
+        if (n == 0) break;
+        if (atomicCAS(&W.work[1], h, h + 1u) == h) { chunk = h; count = n; break; }
+      }
+      if (chunk == kNone && primaryLeft) base = atomicAdd(&W.work[0], 32u);      // (2) a primary batch
+    }
+    chunk = __shfl_sync(kFull, chunk, 0);
+    count = __shfl_sync(kFull, count, 0);
+    base = __shfl_sync(kFull, base, 0);
+    const bool anyPhase = chunk != kNone;
+    if (!anyPhase && (base == kNone || base >= nWork)) {           // (3) nothing to do right now
+      primaryLeft = false;
+      uint32_t fin = 0;
+      if (lane == 0 && ldRelaxed(&W.work[5]) == nBatches) {
+        const uint32_t t = ldRelaxed(&W.work[2]);
+        fin = 32u * ldRelaxed(&W.work[1]) >= t ? 1u : 0u;
+      }
+      if (__shfl_sync(kFull, fin, 0)) break;
+      // (safety net, never reached in a correct run: ~3 s of idling ends the warp and raises work[6] instead of
+      // hanging the device)
+      if (++idle > (1u << 24)) { if (lane == 0) atomicExch(&W.work[6], 1u); break; }
+      __nanosleep(200);
+      continue;
+    }
+    // ---- set up the walk: a probe of the chunk, or the camera ray of an item ----------------------------------------
+    Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    YB_CNT_INIT(s);
+    bool busy = false, valid = false;
+    int u = 0, v = 0;
+    uint32_t sLocal = 0, item = 0, outIndex = 0;
+    const uint32_t entry = 32u * chunk + lane;
+    if (anyPhase) {
+      valid = lane < count;
+      if (valid) {
+        const float4 a = __ldcg(&W.q0[entry]);
+        outIndex = __float_as_uint(a.w);
+        // illuminationAtPoint's probe (Lights.hs:20-24) from its origin: direction and length as shadeAndEmit computes them
+        const V3 p0 = mk(a.x, a.y, a.z);
+        const V3 dl = vsub(xyz(__ldg(&sc.lights[0])), p0);
+        r = makeRay(p0, vnorm(dl));
+        busy = travBegin(sc, r, len(dl), s);
+      }
+    } else {
+      sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+      item = base - sLocal * W.itemsPadded + lane;
+      valid = item < W.nItems;
+      if (valid) {
+        itemPixel(W, item, u, v);
+        r = itemRay(W, u, v, W.sample + sLocal);
+        busy = travBegin(sc, r, 1e6f, s);
+      }
+    }
+    traverseWarpWide<false>(sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, anyPhase);
+    flushCounts(W, s, anyPhase ? 1 : 0, !anyPhase && valid && s.best != kNoHit);
+    if (anyPhase) {
+      // ---- result of the probes: every pixel of the chunk is stored exactly once, here ------------------------------
+      uint32_t row = 0;
+      if (valid) {
+        const float4 c = __ldcg(&W.q2[entry]);
+        const bool unoccluded = s.best == kNoHit;
+        const uint32_t flags = __float_as_uint(c.w);
+        const float qnan = __uint_as_float(0x7FFFFFFFu);
+        storeFinal(W, (size_t)outIndex, (flags & 1u) ? qnan : 0.0f + (unoccluded ? c.x : 0.0f),
+                   (flags & 2u) ? qnan : 0.0f + (unoccluded ? c.y : 0.0f),
+                   (flags & 4u) ? qnan : 0.0f + (unoccluded ? c.z : 0.0f));
+        row = flags >> 3;
+      }
+      __syncwarp();
+      if (lane == 0) W.commit[chunk] = 0u;                         // clean for the next launch
+      if (W.discardQueue && count == 32u && lane < 8u) {           // 2 x 512 B = 8 lines of 128 B, read and done with
+        const char* line = (lane < 4u ? (const char*)(W.q0 + 32u * (size_t)chunk) : (const char*)(W.q2 + 32u * (size_t)chunk)) +
+                           128u * (lane & 3u);
+        asm volatile("discard.global.L2 [%0], 128;" :: "l"(line) : "memory");
+      }
+      if (W.rowFlags) rowsSignal(W, row, valid, lane);
+    } else {
+      // ---- shading; the probes of the batch go to the queue ----------------------------------------------------------
+      LocalProbe pr;
+      pr.emit = false; pr.nanBits = 0; pr.row = 0; pr.tMax = 0.0f;
+      pr.origin = mk(0, 0, 0); pr.dir = mk(0, 0, 1); pr.contrib = mk(0, 0, 0);
+      const uint32_t pixel = (uint32_t)(W.base.width * v + u);
+      shadeAndEmit<false, true>(W, valid, item, pixel, v, r, s.tMax, s.best, lane, sLocal, &pr);
+      const unsigned m = __ballot_sync(kFull, pr.emit);
+      if (m) {
+        const uint32_t n = (uint32_t)__popc(m);
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&W.work[2], n);
+        first = __shfl_sync(kFull, first, 0);
+        if (pr.emit) {
+          const uint32_t e = first + (uint32_t)__popc(m & ((1u << lane) - 1u));
+          __stcg(&W.q0[e], make_float4(pr.origin.x, pr.origin.y, pr.origin.z, __uint_as_float(sLocal * W.framePixels + pixel)));
+          __stcg(&W.q2[e], make_float4(pr.contrib.x, pr.contrib.y, pr.contrib.z, __uint_as_float(pr.nanBits | (pr.row << 3))));
+        }
+        __syncwarp();
+        if (lane == 0) {                                           // commit: the append touches one or two chunks
+          const uint32_t c0 = first >> 5, inFirst = 32u - (first & 31u);
+          if (n <= inFirst) addRelease(&W.commit[c0], n);
+          else { addRelease(&W.commit[c0], inFirst); addRelease(&W.commit[c0 + 1u], n - inFirst); }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) addRelease(&W.work[5], 1u);                   // after the commits, in program order
+      if (W.rowFlags) rowsSignal(W, pr.row, valid && !pr.emit, lane);            // final without a probe
+    }
+  }
+}
+
+#ifndef YB_COUNT_WORK
 // ---------------------------------------------------------------------------------------------
 // Whitted recursion (recursionDepth >= 2, Integrators.hs:22-47) for ONE point light, on the same plan as k_wf_fused: a
 // warp takes a batch through level after level -- closest-hit walk, shading, any-hit walk of the level's shadow probe,
@@ -663,7 +925,7 @@ constexpr int kMaxLevels = 16;             // YAHR_B200_MAX_RECURSION
 
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
+  YB_STACK(0);
   V3 weight[kMaxLevels], direct[kMaxLevels];
   const unsigned lane = threadIdx.x & 31u;
   const int depth = W.base.depth;
@@ -726,8 +988,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid
     if (valid) {
       V3 acc = mk(0.0f, 0.0f, 0.0f);
       for (int k = levels - 1; k >= 0; --k) acc = vadd(vmul(weight[k], acc), direct[k]);
-      float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
-      out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;
+      storeFinal(W, (size_t)(sLocal * W.framePixels + pixel), acc.x, acc.y, acc.z);
     }
     if (W.rowFlags) rowsSignal(W, valid ? (uint32_t)W.rowOfV[v] : 0u, valid, lane);       // streamed host output
     const uint32_t wp = __reduce_add_sync(kFull, nProbes), ws = __reduce_add_sync(kFull, nSecondary);
@@ -741,7 +1002,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid
 // (ray, primitive, t) of the hit is kept; the surface, frame and material are rebuilt from them before each probe.
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
+  YB_STACK(0);
   V3 weight[kMaxLevels], direct[kMaxLevels];
   const unsigned lane = threadIdx.x & 31u;
   const DeviceScene& sc = W.base.sc;
@@ -832,8 +1093,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const
     if (valid) {
       V3 acc = mk(0.0f, 0.0f, 0.0f);
       for (int k = levels - 1; k >= 0; --k) acc = vadd(vmul(weight[k], acc), direct[k]);
-      float* out = W.sampleOut + 3 * (size_t)(sLocal * W.framePixels + pixel);
-      out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;
+      storeFinal(W, (size_t)(sLocal * W.framePixels + pixel), acc.x, acc.y, acc.z);
     }
     if (W.rowFlags) rowsSignal(W, valid ? (uint32_t)W.rowOfV[v] : 0u, valid, lane);       // streamed host output
     const uint32_t wp = __reduce_add_sync(kFull, nProbes), ws = __reduce_add_sync(kFull, nSecondary);
@@ -842,10 +1102,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const
   }
 }
 
+#endif   // !YB_COUNT_WORK
+
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, bool WIDE, int MIN_BLOCKS>
+template <bool ORDERED, bool WIDE, int MIN_BLOCKS, int SH>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
-  uint2 stack[64];
+  YB_STACK(SH);
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t nEntries = W.dense ? W.nItems * W.samplesPerLaunch * W.base.sc.nSlots : W.work[2];
   for (;;) {
@@ -857,6 +1119,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
     Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     Trav s;
     s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    YB_CNT_INIT(s);
     bool busy = false, probe = false;
     if (entry < nEntries) {
       const float4 a = W.q0[entry], b = W.q1[entry];
@@ -870,6 +1133,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
     }
     if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
+    flushCounts(W, s, 1, false);
     uint32_t row = 0;
     if (probe) row = shadowResult(W, entry, s.best == kNoHit);
     if (W.rowFlags) rowsSignal(W, row, probe, lane);
@@ -915,6 +1179,7 @@ __global__ void __launch_bounds__(256) k_wf_accum(const __grid_constant__ Wavefr
   }
 }
 
+#ifndef YB_COUNT_WORK
 // item -> pixel table of a tile set (built once, when the tile set is first used)
 __global__ void __launch_bounds__(256) k_wf_pixel_table(const __grid_constant__ WavefrontParams W, uint32_t* table) {
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -930,6 +1195,7 @@ cudaError_t launchPixelTable(WavefrontParams W, uint32_t* table, cudaStream_t st
   k_wf_pixel_table<<<(W.nItems + 255u) / 256u, 256, 0, stream>>>(W, table);
   return cudaGetLastError();
 }
+#endif
 
 __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   // ray counters for the stats: primary = items, shadow = probes emitted
@@ -937,7 +1203,7 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
   atomicAdd(&W.base.counters[1], (unsigned long long)W.work[3]);
   atomicAdd(&W.base.counters[2], (unsigned long long)W.work[4]);
   if (W.bandStat) *W.bandStat += W.work[3];
-  W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0; W.work[4] = 0;      // ready for the next launch
+  W.work[0] = 0; W.work[1] = 0; W.work[2] = 0; W.work[3] = 0; W.work[4] = 0; W.work[5] = 0;   // ready for the next launch
 }
 
 // Persistent launch: exactly as many 128-thread CTAs as can be resident (occupancy API), so that every
@@ -952,12 +1218,21 @@ static void launchPersistent(void (*kernel)(WavefrontParams), const WavefrontPar
   kernel<<<numSMs * perSM, 128, 0, stream>>>(W);
 }
 
+// kernel<..., SH> for the run-time choice of shared-memory stack entries per lane (0, 8, 12)
+#define YB_PICK_SH(sh, K0, K8, K12) ((sh) >= 12u ? (K12) : ((sh) >= 8u ? (K8) : (K0)))
+
+#ifdef YB_COUNT_WORK
+cudaError_t launchWavefrontCounted(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
+                                   cudaEvent_t* phaseEvents) {
+#else
 cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
                             cudaEvent_t* phaseEvents) {
+#endif
   if (W.nItems == 0) return cudaSuccess;
   const bool ordered = W.base.traversal == 1;
   const uint32_t itemBlocks = (W.nItems + 255u) / 256u;
   const uint32_t perLaunch = W.samplesPerLaunch ? W.samplesPerLaunch : 1u;
+  const uint32_t sh = W.stackShared;
   W.itemsPadded = (W.nItems + 31u) & ~31u;
   W.framePixels = (uint32_t)(W.base.width * W.base.height);
   for (int s = 0; s < W.base.spp; s += (int)perLaunch) {
@@ -969,55 +1244,68 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
     // AREA: the scene has area lights (extension); kept out of the default instantiation
     const bool area = W.base.sc.nAreaLights != 0;
+    auto tail = [&]() {
+      if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
+      k_wf_count<<<1, 1, 0, stream>>>(W);
+      if (launches) *launches += 1;
+    };
+    auto singleKernelEvents = [&]() {
+      if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
+      if (launches) *launches += 1;
+    };
+#ifndef YB_COUNT_WORK
     if (W.base.depth != 1) {
       // recursion: the per-batch kernels (planFrame admits them for point lights only, on the 4-wide tree)
       if (W.base.sc.nLights == 1) launchPersistent(k_wf_fused_depth<6>, W, numSMs, stream);
       else launchPersistent(k_wf_fused_depth_lights<6>, W, numSMs, stream);
-      if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
-      if (launches) *launches += 1;
-      if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
-      k_wf_count<<<1, 1, 0, stream>>>(W);
-      if (launches) *launches += 1;
+      singleKernelEvents();
+      tail();
       continue;
     }
-    const bool fused = wide && !area && !W.dense && W.fused;
-    if (fused) {
+#endif
+    const bool oneSlot = wide && !area && !W.dense;
+    if (oneSlot && W.persist) {
+      launchPersistent(YB_PICK_SH(sh, (k_wf_persist<8, 0>), (k_wf_persist<8, 8>), (k_wf_persist<8, 12>)), W, numSMs, stream);
+      singleKernelEvents();
+      tail();
+      continue;
+    }
+#ifndef YB_COUNT_WORK
+    if (oneSlot && W.fused) {
       if (W.fused & 2u) launchPersistent(k_wf_fused<7>, W, numSMs, stream);     // experiment: 72 registers
       else launchPersistent(k_wf_fused<8>, W, numSMs, stream);
-      if (timed) { cudaEventRecord(phaseEvents[1], stream); cudaEventRecord(phaseEvents[2], stream); cudaEventRecord(phaseEvents[3], stream); }
-      if (launches) *launches += 1;
-      if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
-      k_wf_count<<<1, 1, 0, stream>>>(W);
-      if (launches) *launches += 1;
+      singleKernelEvents();
+      tail();
       continue;
     }
+#endif
     if (area)
-      launchPersistent(wide ? k_wf_primary<false, 8, true, true>
-                            : (ordered ? k_wf_primary<true, 8, false, true> : k_wf_primary<false, 8, false, true>),
+      launchPersistent(wide ? k_wf_primary<false, 8, true, true, 0>
+                            : (ordered ? k_wf_primary<true, 8, false, true, 0> : k_wf_primary<false, 8, false, true, 0>),
                        W, numSMs, stream);
     else if (wide)
-      launchPersistent(W.capRegisters ? k_wf_primary<false, 8, true, false> : k_wf_primary<false, 1, true, false>, W, numSMs,
-                       stream);
+      launchPersistent(W.capRegisters ? YB_PICK_SH(sh, (k_wf_primary<false, 8, true, false, 0>), (k_wf_primary<false, 8, true, false, 8>),
+                                                   (k_wf_primary<false, 8, true, false, 12>))
+                                      : k_wf_primary<false, 1, true, false, 0>, W, numSMs, stream);
     else
-      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false, false> : k_wf_primary<false, 8, false, false>)
-                                      : (ordered ? k_wf_primary<true, 1, false, false> : k_wf_primary<false, 1, false, false>),
+      launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false, false, 0> : k_wf_primary<false, 8, false, false, 0>)
+                                      : (ordered ? k_wf_primary<true, 1, false, false, 0> : k_wf_primary<false, 1, false, false, 0>),
                        W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
     // 10 CTAs / SM (48 registers) measured 2-3 % faster than the unconstrained 56 registers / 9 CTAs
-    if (wide) launchPersistent(k_wf_shadow<false, true, 10>, W, numSMs, stream);
-    else launchPersistent(ordered ? k_wf_shadow<true, false, 1> : k_wf_shadow<false, false, 1>, W, numSMs, stream);
+    if (wide) launchPersistent(YB_PICK_SH(sh, (k_wf_shadow<false, true, 10, 0>), (k_wf_shadow<false, true, 10, 8>),
+                                          (k_wf_shadow<false, true, 10, 12>)), W, numSMs, stream);
+    else launchPersistent(ordered ? k_wf_shadow<true, false, 1, 0> : k_wf_shadow<false, false, 1, 0>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;
     if (W.dense) {
       k_wf_resolve<<<(W.nItems * W.samplesPerLaunch + 255u) / 256u, 256, 0, stream>>>(W);
       if (launches) *launches += 1;
     }
-    if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
-    k_wf_count<<<1, 1, 0, stream>>>(W);
-    if (launches) *launches += 1;
+    tail();
   }
   return cudaGetLastError();
 }
 
-}  // namespace yb
+YB_WF_CLOSE

@@ -42,7 +42,11 @@ class TileShardedRenderer:
         self.cam = cam
         self.width, self.height = api.image_size(cam)
         self.mode = mode if self.world > 1 else "local"
+        import time
+        t0 = time.time()
         self.scene = api.Scene(scene)
+        torch.cuda.synchronize()
+        t1 = time.time()
         dev = torch.device("cuda", torch.cuda.current_device())
         shape = (self.height, self.width, 3)
         self.want_primid = want_primid
@@ -50,6 +54,7 @@ class TileShardedRenderer:
         self.primid = None
         self._peer_rgb = None     # "p2p": rank 0's frame as seen from this rank
         self._peer_pid = None
+        self._peer_base_rgb = self._peer_base_pid = None
         self._fence = torch.zeros(1, dtype=torch.float32, device=dev)
         if self.mode in ("local", "reduce") or self.rank == 0:
             self.frame = torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -89,8 +94,20 @@ class TileShardedRenderer:
                         q = p
                     else:
                         api._check(L.yahr_b200_ipc_open(hp, C.byref(q)))
+                        self._peer_base_pid = q.value          # a mapping of its own: closed in close()
                     self._peer_pid = q.value + off_pid
             dist.barrier(group=group)
+        torch.cuda.synchronize()
+        # scene_ms: BVH build + upload through the C ABI; exchange_ms: frame buffers, IPC handles, handshake
+        self.timing = {"scene_ms": (t1 - t0) * 1e3, "exchange_ms": (time.time() - t1) * 1e3}
+
+    def work_counts(self, **kw):
+        """The GPU's own work counters for this rank's share (counting build of the default kernels)."""
+        torch = self.torch
+        scratch = torch.empty((self.height, self.width, 3), dtype=torch.float32, device="cuda")
+        return self.scene.render_device_counted(self.cam, scratch.data_ptr(), tile_stride=self.world, tile_offset=self.rank,
+                                                stream=torch.cuda.current_stream().cuda_stream,
+                                                by_rows=(self.mode == "rows"), **kw)
 
     def _alloc_offset(self, t):
         """Offset of a tensor inside its cudaMalloc block (cudaIpcGetMemHandle refers to the block)."""
@@ -110,7 +127,13 @@ class TileShardedRenderer:
 
     def render(self, recursion_depth=1, spp=1, seed=0, traversal=api.TRAVERSAL_REFERENCE, kernel=0, tune=0):
         """Enqueue one frame on the current stream; the frame is complete on rank 0 once the
-        stream has drained.  Returns nothing (no host sync)."""
+        stream has drained.  Returns nothing (no host sync).
+
+        Frame ownership: there is ONE gather frame on rank 0 and the other ranks write into it directly ("p2p": remote
+        stores from the kernels, "rows": device-to-device pushes).  The fence at the end orders the completion of THIS
+        frame only, so rank 0 must have finished reading frame N (on the render stream, or synchronised with it) before
+        any rank calls render() for frame N + 1 -- e.g. a barrier after the consumer, as bench.py and tests/dist_check.py
+        do.  The "reduce" mode has no such constraint (every rank owns its frame)."""
         torch, dist = self.torch, self.dist
         stream = torch.cuda.current_stream().cuda_stream
         kw = dict(recursion_depth=recursion_depth, spp=spp, seed=seed, traversal=traversal, stream=stream,
@@ -164,7 +187,9 @@ class TileShardedRenderer:
         if self._peer_rgb is not None:
             import ctypes as C
             api.lib().yahr_b200_ipc_close(C.c_void_p(self._peer_base_rgb))
-            self._peer_rgb = None
+            if self._peer_base_pid is not None:
+                api.lib().yahr_b200_ipc_close(C.c_void_p(self._peer_base_pid))
+            self._peer_rgb = self._peer_pid = self._peer_base_pid = None
         self.scene.close()
 
 
@@ -179,15 +204,19 @@ class SharedHostFrame:
         from multiprocessing import shared_memory
         self.rank, self.world = rank, world
         self.nbytes = int(width) * int(height) * 12
-        name = name or ("yahr_b200_frame_%s" % os.environ.get("MASTER_PORT", "0"))
         self._owner = rank == 0
+        if name is None:
+            # a name nobody else can hold: rank 0 draws it (pid + random suffix) and tells the others, so that no
+            # existing segment is ever unlinked on a guess
+            names = [None]
+            if self._owner:
+                import uuid
+                names = ["yahr_b200_frame_%d_%s" % (os.getpid(), uuid.uuid4().hex[:12])]
+            if world > 1:
+                import torch.distributed as dist
+                dist.broadcast_object_list(names, src=0)
+            name = names[0]
         if self._owner:
-            try:
-                stale = shared_memory.SharedMemory(name=name)
-                stale.close()
-                stale.unlink()
-            except FileNotFoundError:
-                pass
             self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.nbytes)
         if barrier:
             barrier()
