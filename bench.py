@@ -555,6 +555,25 @@ def run_ours(args):
         e2e_ms = float(tt.mean()) * 1e3
         if rank == 0:
             host_frames = {"e2e_float": host.array.copy()}
+        # the same with the reference's 8-bit output stage on the GPU (what the CLI writes): a quarter of the bytes
+        frame8 = host.array.reshape(-1).view(np.uint8)[:h * w * 3].reshape(h, w, 3)
+        t8 = []
+        for i in range(e2e_warmup + args.steps):
+            flush.zero_()
+            barrier()
+            t = time.perf_counter()
+            st8 = R.scene.render_shard_rgb8(cam, rank, world, frame8, recursion_depth=args.depth, spp=args.spp)
+            dt = time.perf_counter() - t
+            if i >= e2e_warmup:
+                t8.append(dt)
+        tt8 = torch.tensor(t8, dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt8, op=dist.ReduceOp.MAX)
+        b8 = torch.tensor([float(st8["d2h_bytes"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(b8)
+        barrier()
+        if rank == 0:
+            host_frames["e2e_rgb8"] = frame8.copy()
+        rgb8_ms = float(tt8.mean()) * 1e3
         e2e = {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(bytes_t[0]), "d2h_bytes_per_step": int(bytes_t[1]),
                "api": "yahr_b200_render_shard on every rank (tile rows r mod N == rank) into one shared pinned host frame"
@@ -562,6 +581,9 @@ def run_ours(args):
                "launches_per_call": int(ste["launches"]),
                "strategy": ("streamed rows (fused kernel, finished tile rows copied while the frame is traced)"
                             if ste["launches"] <= 3 else "copy-engine bands") + " -- static rule of the entry (1 light slot, 1 spp -> streamed)",
+               "rgb8": {"value": rays_total / (rgb8_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": rgb8_ms,
+                        "d2h_bytes_per_step": int(b8[0]),
+                        "api": "yahr_b200_render_shard_rgb8 on every rank (8-bit output stage on the GPU, as the yahr CLI does)"},
                "scene_create_ms": R.timing["scene_ms"], "exchange_setup_ms": R.timing["exchange_ms"],
                "renderer_init_ms": create_s * 1e3, "scene_upload_bytes": int(info["device_bytes"])}
         host.close()

@@ -212,6 +212,20 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
 int yahr_b200_render_shard(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
                            int shard_index, int shard_count, float* rgb_out, uint32_t* primid_out, yahr_stats* stats);
 
+/* The same with the reference's 8-bit output stage (main.hs:142) applied on the GPU: rgb8_out is the FULL-frame
+ * W*H*3 byte buffer shared by the shards; a quarter of the bytes cross PCIe. */
+int yahr_b200_render_shard_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                                int shard_index, int shard_count, unsigned char* rgb8_out, yahr_stats* stats);
+
+/* End-of-frame fence of the multi-GPU device-buffer exchange (the reference's `concat`, main.hs:83,95, has no
+ * counterpart for it: its sparks share one heap).  A pushing rank enqueues yahr_b200_flag_signal on the stream its
+ * stores / copies into rank 0's frame ran on: `value` (the frame's sequence number, growing) is written to d_flag --
+ * this rank's word of an array in rank 0's memory, mapped with yahr_b200_ipc_open -- after a system-scope fence.
+ * Rank 0 enqueues yahr_b200_flags_wait on the stream that consumes the frame: the stream blocks until the `count`
+ * words from `first` on have all reached `value` (it gives up after ~4 s rather than hang the device). */
+int yahr_b200_flag_signal(uint32_t* d_flag, uint32_t value, void* stream);
+int yahr_b200_flags_wait(uint32_t* d_flags, int first, int count, uint32_t value, void* stream);
+
 /* Same frame with the reference's output stage applied on the GPU: JuicyPixels' ImageRGBF -> 8-bit
  * conversion used by savePngImage (main.hs:142), truncate (255 * max 0 (min 1 x)), no gamma.
  * rgb8_out: W*H*3 bytes, row-major, row 0 = top.  Only a quarter of the bytes cross PCIe. */

@@ -303,6 +303,22 @@ class Scene:
                                         C.byref(st)))
         return st.as_dict()
 
+    def render_shard_rgb8(self, cam, shard_index, shard_count, out, recursion_depth=1, spp=1, seed=0):
+        """yahr_b200_render_shard_rgb8: this shard's tile rows of the 8-bit frame into the full-frame host buffer
+        out ([H,W,3] uint8, or a raw address)."""
+        c = make_camera(cam)
+        w, h = int(np.floor(c.imW)), int(np.floor(c.imH))
+        if hasattr(out, "ctypes"):
+            _check_out(out, (h, w, 3), np.uint8, "out (rgb8)")
+        st = Stats()
+        L = lib()
+        L.yahr_b200_render_shard_rgb8.restype = C.c_int
+        L.yahr_b200_render_shard_rgb8.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                                  C.c_int, C.c_void_p, C.POINTER(Stats)]
+        _check(L.yahr_b200_render_shard_rgb8(self._h, C.byref(c), recursion_depth, spp, seed, shard_index, shard_count,
+                                             out.ctypes.data if hasattr(out, "ctypes") else int(out), C.byref(st)))
+        return st.as_dict()
+
     def download_bvh(self):
         """(order[n_prims], nodes[n_nodes,16] float32 raw, multi[n_multi,2], root_ref, root_box[6])."""
         i = self.info()

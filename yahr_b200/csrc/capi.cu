@@ -121,7 +121,6 @@ struct yahr_scene {
   // two slots so that consecutive bands of the host-buffer entry can be in flight on two streams
   float4 *wfQ0[2] = {nullptr, nullptr}, *wfQ1[2] = {nullptr, nullptr}, *wfQ2[2] = {nullptr, nullptr};
   unsigned char* wfVis[2] = {nullptr, nullptr};
-  uint32_t* wfCommit[2] = {nullptr, nullptr};   // k_wf_persist: per chunk of 32 queue entries, entries written (zero between launches)
   size_t wfEntries[2] = {0, 0};
   unsigned long long* d_workStats = nullptr;    // counting build: 16 work counters
   int preferBinary = 0;                         // per-scene choice of the walk: 1 = binary tree, 0 = its 4-wide collapse
@@ -135,7 +134,7 @@ struct yahr_scene {
   size_t framePixels = 0;
   unsigned char* d_rgb8 = nullptr;
   size_t frame8Pixels = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evIn = nullptr;
   cudaEvent_t phaseEv[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t renderStream[2] = {nullptr, nullptr}, copyStream = nullptr;   // host-buffer entry: render / D2H overlap
   std::vector<cudaEvent_t> bandEvents;
@@ -161,11 +160,12 @@ struct yahr_scene {
     }
     cudaFree(d_rowDone);
     if (h_rowFlags) cudaFreeHost(h_rowFlags);
-    for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); cudaFree(wfCommit[k]); }
+    for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
     cudaFree(d_workStats);
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (evIn) cudaEventDestroy(evIn);
     for (auto e : phaseEv) if (e) cudaEventDestroy(e);
     for (auto e : bandEvents) cudaEventDestroy(e);
     for (auto st : renderStream) if (st) cudaStreamDestroy(st);
@@ -372,7 +372,6 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     // bit 15: one light slot -> ONE persistent kernel with committed probe chunks (k_wf_persist); bit 29 = the two-kernel set
     static const int envPersist = getenv("YAHR_B200_PERSIST") ? atoi(getenv("YAHR_B200_PERSIST")) : -1;
     W.persist = (tune & 0x20000000u) ? 0u : ((tune & 0x8000u) ? 1u : (envPersist >= 0 ? (uint32_t)envPersist : kDefaultPersist));
-    W.discardQueue = ((tune >> 28) & 1u) ^ 1u;     // default: consumed queue lines are discarded from L2 (bit 28 set = kept)
     // bits 24-27: traversal-stack entries per lane in shared memory: 0 = default, 1 = none (all local), 8, 12
     static const int envSh = getenv("YAHR_B200_STACK_SH") ? atoi(getenv("YAHR_B200_STACK_SH")) : -1;
     const uint32_t shBits = (tune >> 24) & 0xFu;
@@ -391,8 +390,10 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
   if (plan.wavefront) {
     WavefrontParams W = plan.W;
     // (the recursion kernels keep their probes in registers: no queue)
-    const size_t entries = plan.P.depth != 1 ? 0 : (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) *
-                                                       plan.entriesPerItem * plan.samplesPerLaunch;
+    size_t entries = plan.P.depth != 1 ? 0 : (size_t)(ts.hostStart[first + count] - ts.hostStart[first]) *
+                                                 plan.entriesPerItem * plan.samplesPerLaunch;
+    // k_wf_persist keeps a 256-entry ring per CTA in q0 / q2 instead (at most 16 CTAs per SM)
+    if (plan.P.depth == 1 && W.persist && entries < (size_t)sc->numSMs * 16 * 256) entries = (size_t)sc->numSMs * 16 * 256;
     if (entries > sc->wfEntries[slot]) {          // grows only on the first frame of a given size
       CU(cudaDeviceSynchronize());
       cudaFree(sc->wfQ0[slot]); cudaFree(sc->wfQ1[slot]); cudaFree(sc->wfQ2[slot]); cudaFree(sc->wfVis[slot]);
@@ -401,12 +402,9 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
       CU(cudaMalloc(&sc->wfQ1[slot], entries * sizeof(float4)));
       CU(cudaMalloc(&sc->wfQ2[slot], entries * sizeof(float4)));
       CU(cudaMalloc(&sc->wfVis[slot], entries));
-      cudaFree(sc->wfCommit[slot]); sc->wfCommit[slot] = nullptr;
-      CU(cudaMalloc(&sc->wfCommit[slot], (entries / 32 + 2) * sizeof(uint32_t)));
-      CU(cudaMemset(sc->wfCommit[slot], 0, (entries / 32 + 2) * sizeof(uint32_t)));
       sc->wfEntries[slot] = entries;
     }
-    W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot]; W.commit = sc->wfCommit[slot];
+    W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot];
     W.visibility = plan.entriesPerItem > 1 ? sc->wfVis[slot] : nullptr;
     W.work = sc->wfWork + 8 * slot;
     W.bandStat = bandStat;
@@ -864,6 +862,9 @@ int yahr_b200_render_device_counted(yahr_scene* scene, const yahr_camera* cam, c
   }
 }
 
+static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_out, unsigned char* rgb8_out,
+                               uint32_t* primid_out, yahr_stats* stats, double w0, double copyBytesPerMs);
+
 // Device-buffer multi-GPU entry: render the tile rows of this shard into the LOCAL frame, then push exactly those
 // pixel rows into the gather frame (usually rank 0's, mapped with yahr_b200_ipc_open) with device-to-device copies on
 // the same stream: a few large NVLink transfers instead of one small remote store per pixel.
@@ -877,6 +878,34 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
     yahr_render_opts o = *opts_in;
     o.tile_stride = shard_count; o.tile_offset = shard_index; o.reserved[1] = 1;      // whole rows of the tile grid
     cudaStream_t st = (cudaStream_t)stream;
+    // STREAMED push (one light slot, 1 spp, a gather frame that is not the local one): ONE launch of the per-batch
+    // kernel; every finished tile row is copied into the gather frame by the copy engine while the rest of the share
+    // is traced (the mechanism of the host-buffer entry, renderStreamedRows, with a peer frame as the destination), so
+    // the exchange overlaps the rendering instead of following it.  The call then returns when this shard's rows ARE in
+    // the gather frame (it blocks the host thread; work enqueued on `stream` before / after it is ordered before / after).
+    // YAHR_B200_SHARD_STREAM=0 keeps the render-then-push path below.
+    {
+      const bool push = (d_rgb_gather && d_rgb_gather != d_rgb_local);
+      const char* env = getenv("YAHR_B200_SHARD_STREAM");
+      if (push && !(env && atoi(env) == 0) && o.spp == 1 && !stats) {
+        FramePlan plan;
+        int prc = planFrame(scene, cam, &o, d_rgb_local, d_primid_local, plan);
+        if (prc) return prc;
+        const TileSet& pts = *plan.ts;
+        const bool pushPid0 = d_primid_gather && d_primid_local && d_primid_gather != d_primid_local;
+        if (plan.wavefront && !plan.W.dense && pts.rowY.size() >= 2 && pts.d_rowOfV && scene->dev.wide &&
+            scene->dev.nAreaLights == 0 && plan.W.wideTree && o.traversal == YAHR_TRAVERSAL_REFERENCE) {
+          for (auto& s2 : scene->renderStream) if (!s2) CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+          if (!scene->copyStream) CU(cudaStreamCreateWithFlags(&scene->copyStream, cudaStreamNonBlocking));
+          if (!scene->evIn) CU(cudaEventCreateWithFlags(&scene->evIn, cudaEventDisableTiming));
+          CU(cudaEventRecord(scene->evIn, st));
+          CU(cudaStreamWaitEvent(scene->renderStream[0], scene->evIn, 0));
+          renderStreamedRows(scene, plan, d_rgb_gather, nullptr, pushPid0 ? d_primid_gather : nullptr, nullptr, nowMs(),
+                             400.0e6);
+          return YAHR_OK;                      // both internal streams have been synchronised: nothing left in flight
+        }
+      }
+    }
     int rc = renderCommon(scene, cam, &o, d_rgb_local, d_primid_local, st, nullptr, false);
     if (rc) return rc;
     CameraSetup cs;
@@ -947,7 +976,7 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
 // granularity and the persistent kernel pays its ramp-up and tail once (bands: once per band).  If the kernel ends
 // before every flag has been seen the remaining rows are simply copied then: the accounting can never lose a row.
 static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_out, unsigned char* rgb8_out,
-                               uint32_t* primid_out, yahr_stats* stats, double w0) {
+                               uint32_t* primid_out, yahr_stats* stats, double w0, double copyBytesPerMs) {
   const TileSet& ts = *plan.ts;
   const uint32_t nRowsS = (uint32_t)ts.rowY.size();
   const int W_ = plan.cs.width;
@@ -988,15 +1017,17 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
   uint32_t nCopies = 0;
   const size_t rowBytes = (size_t)W_ * 3 * (rgb8_out ? 1 : sizeof(float)), idBytes = (size_t)W_ * sizeof(uint32_t);
   char* const hostFrame = rgb8_out ? (char*)rgb8_out : (char*)rgb_out;
-  const char* const devFrame = rgb8_out ? (const char*)scene->d_rgb8 : (const char*)scene->d_rgb;
+  // the frame the kernels of this plan render into (the library's own frame for the host-buffer entry, the caller's
+  // local frame for the device shard entry); destinations may be host memory or a peer GPU's frame (UVA decides)
+  const char* const devFrame = rgb8_out ? (const char*)scene->d_rgb8 : (const char*)plan.W.base.rgb;
   auto copyRows = [&](uint32_t r, uint32_t e) {
     const int y0 = ts.rowY[r].x, y1 = ts.rowY[e - 1].y;
     CU(cudaMemcpyAsync(hostFrame + (size_t)y0 * rowBytes, devFrame + (size_t)y0 * rowBytes,
-                       (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, cp));
+                       (size_t)(y1 - y0) * rowBytes, cudaMemcpyDefault, cp));
     d2h += (uint64_t)(y1 - y0) * rowBytes;
     if (primid_out) {
-      CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)scene->d_primid + (size_t)y0 * idBytes,
-                         (size_t)(y1 - y0) * idBytes, cudaMemcpyDeviceToHost, cp));
+      CU(cudaMemcpyAsync((char*)primid_out + (size_t)y0 * idBytes, (const char*)plan.W.base.primid + (size_t)y0 * idBytes,
+                         (size_t)(y1 - y0) * idBytes, cudaMemcpyDefault, cp));
       d2h += (uint64_t)(y1 - y0) * idBytes;
     }
     ++nCopies;
@@ -1032,7 +1063,7 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
       const double now = nowMs();
       if (!kernelsDone && canGrow && bytes < maxHeldBytes && busyUntil - now > 0.05) { r = e; continue; }
       copyRows(r, e);
-      busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / 48.0e6 + 0.008;    // measured under load
+      busyUntil = (busyUntil > now ? busyUntil : now) + (double)bytes / copyBytesPerMs + 0.008;    // measured under load
       if (!kernelsDone) flaggedRows += e - r;
       for (uint32_t k = r; k < e; ++k) issued[k] = 1;
       nIssued += e - r;
@@ -1151,7 +1182,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
         useStream = strategy->wantStream();
       }
       if (useStream) {
-        renderStreamedRows(scene, plan, rgb_out, rgb8_out, primid_out, stats, w0);
+        renderStreamedRows(scene, plan, rgb_out, rgb8_out, primid_out, stats, w0, 48.0e6);
         if (strategy) strategy->record(true, nowMs() - w0);
         return YAHR_OK;
       }
@@ -1326,6 +1357,35 @@ int yahr_b200_render_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursi
                           unsigned char* rgb8_out, yahr_stats* stats) {
   if (!rgb8_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb8_out is NULL");
   return renderHost(scene, cam, recursion_depth, spp, seed, nullptr, rgb8_out, nullptr, stats);
+}
+
+int yahr_b200_render_shard_rgb8(yahr_scene* scene, const yahr_camera* cam, int recursion_depth, int spp, uint64_t seed,
+                                int shard_index, int shard_count, unsigned char* rgb8_out, yahr_stats* stats) {
+  if (!rgb8_out) return fail(YAHR_ERR_INVALID_ARGUMENT, "rgb8_out is NULL");
+  return renderHost(scene, cam, recursion_depth, spp, seed, nullptr, rgb8_out, nullptr, stats, shard_index, shard_count);
+}
+
+// End-of-frame fence of the multi-GPU exchange without a collective: every pushing rank stores the frame's sequence
+// number into ITS word of a flag array in rank 0's memory (mapped with yahr_b200_ipc_open) once its rows have landed;
+// rank 0's stream waits until every word has reached the number.
+int yahr_b200_flag_signal(uint32_t* d_flag, uint32_t value, void* stream) {
+  if (!d_flag) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  try {
+    CU(launchFlagSignal(d_flag, value, (cudaStream_t)stream));
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  }
+}
+
+int yahr_b200_flags_wait(uint32_t* d_flags, int first, int count, uint32_t value, void* stream) {
+  if (!d_flags || first < 0 || count < 0 || count > 1024) return fail(YAHR_ERR_INVALID_ARGUMENT, "invalid argument");
+  try {
+    if (count) CU(launchFlagsWait(d_flags + first, count, value, (cudaStream_t)stream));
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  }
 }
 
 // Pinned host memory for the output buffers: device-to-host copies into it run at full PCIe speed

@@ -106,11 +106,9 @@ struct WavefrontParams {
   uint32_t* rowDone;              // finalised pixels per tile row (zeroed before the launch)
   volatile uint32_t* rowFlags;    // mapped host memory: rowFlags[row] = rowSeq once the row is complete in device memory
   uint32_t rowSeq;
-  // k_wf_persist (one launch per frame): probes are appended to q0 / q2 (32 B each) and consumed in committed chunks of 32
+  // k_wf_persist (one launch per frame): the probes go through a 256-entry ring per CTA in q0 / q2 (32 B per probe)
   uint32_t persist;               // 1: one light slot, depth 1, 4-wide tree -> k_wf_persist instead of primary + shadow
-  uint32_t* commit;               // per chunk of 32 queue entries: entries written so far (all zero between launches)
   uint32_t stackShared;           // traversal-stack entries per lane kept in shared memory (0, 8 or 12)
-  uint32_t discardQueue;          // consumed queue lines are dropped from L2 without write-back (discard.global.L2)
   unsigned long long* workStats;  // counting build only: 2 x 8 work counters (closest-hit walks, any-hit walks); else NULL
   unsigned char* rgb8;            // 8-bit host-buffer entry through the streamed rows: the per-batch kernels store the
                                   // quantised pixel (main.hs:142) here INSTEAD of the float frame; NULL otherwise

@@ -76,6 +76,37 @@ cudaError_t launchQuantizeRgb8(const float* rgb, unsigned char* out, size_t firs
   return cudaGetLastError();
 }
 
+// Multi-GPU end-of-frame fence (yahr_b200_flag_signal / yahr_b200_flags_wait).  The signalling kernel runs after the
+// rank's stores / copies into the gather frame in stream order; the fence makes them visible system-wide before the word.
+__global__ void k_flag_signal(uint32_t* flag, uint32_t value) {
+  __threadfence_system();
+  *(volatile uint32_t*)flag = value;
+}
+
+// One thread per word; sequence numbers only grow (wrap-safe comparison).  A peer that never signals must not hang the
+// device: after ~4 s the wait gives up (the frame is then incomplete and the word is left behind, which the next wait
+// and the caller's frame check will show).
+__global__ void k_flags_wait(uint32_t* flags, int count, uint32_t value) {
+  const int i = (int)threadIdx.x;
+  if (i >= count) return;
+  const long long t0 = clock64();
+  while ((int)(*(volatile uint32_t*)(flags + i) - value) < 0) {
+    __nanosleep(100);
+    if (clock64() - t0 > 8000000000ll) break;
+  }
+  __threadfence_system();
+}
+
+cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+  k_flag_signal<<<1, 1, 0, stream>>>(flag, value);
+  return cudaGetLastError();
+}
+
+cudaError_t launchFlagsWait(uint32_t* flags, int count, uint32_t value, cudaStream_t stream) {
+  k_flags_wait<<<1, count <= 32 ? 32 : ((count + 31) / 32) * 32, 0, stream>>>(flags, count, value);
+  return cudaGetLastError();
+}
+
 cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_t* launches) {
   if (P.nTiles == 0) return cudaSuccess;
   if (P.traversal == 1) k_render_mega<true><<<P.nTiles, 256, 0, stream>>>(P);

@@ -11,6 +11,10 @@ cudaError_t launchRenderMega(const RenderParams& P, cudaStream_t stream, uint32_
 cudaError_t launchQuantizeRgb8(const float* rgb, unsigned char* out, size_t first, size_t count, cudaStream_t stream,
                                uint32_t* launches);
 
+// Multi-GPU end-of-frame fence: one word per pushing rank in rank 0's memory.
+cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+cudaError_t launchFlagsWait(uint32_t* flags, int count, uint32_t value, cudaStream_t stream);
+
 }  // namespace yb
 
 namespace yb {

@@ -715,76 +715,91 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_const
 
 // ---------------------------------------------------------------------------------------------
 // ONE persistent kernel per frame for one light slot (the reference's configuration), with COMMITTED PROBE CHUNKS.
-// Every warp loops: (1) if a full chunk of 32 shadow probes is committed in the queue, claim it and run the any-hit
-// walks (reachable, Rays.hs:49-54) of those 32 probes -- compacted across batches, like k_wf_shadow; (2) else take a
-// batch of 32 primary items: camera rays, closest-hit walk, shading (as k_wf_primary), append the probes of the batch
-// to the queue (one atomic per warp) and COMMIT them: a release-add of the number of entries written to the counter of
-// each chunk the append touched.  A chunk is claimed only once its counter says it is complete, so nobody ever waits
-// for a producer; the last, partial chunk becomes claimable when every primary batch has committed (work[5]).
+// Every warp loops: (1) if its CTA holds a complete chunk of 32 shadow probes, claim it and run the any-hit walks
+// (reachable, Rays.hs:49-54) of those 32 probes -- compacted across the CTA's batches, at k_wf_shadow's lane
+// occupancy; (2) else take a batch of 32 primary items from the global counter: camera rays, closest-hit walk, shading
+// (as k_wf_primary), append the probes of the batch to the CTA's ring (one shared-memory atomic per warp) and COMMIT
+// them: add the number of entries written to the counter of each chunk the append touched.  A chunk is claimed only
+// once its counter says it is complete, so nobody waits for a producer; the partial chunk a CTA is left with at the
+// end is walked once every warp of the CTA has run out of primary work.
 //   * one launch: one ramp-up and one tail per frame, and the tail of the primary trace (the long horizon rays)
-//     overlaps the any-hit walks of the rest -- what a 1/N share of a frame on N GPUs needs most;
-//   * a probe is consumed microseconds after it was written: the queue lives in L2 (32 B per probe: origin + pixel,
-//     contribution + flags; direction and length are recomputed from the light), and the consumed lines are
-//     discarded from L2 so they are never written back to HBM;
+//     overlaps the any-hit walks -- what a 1/N share of a frame on N GPUs needs most;
+//   * the queue is a 256-entry ring PER CTA (32 B per probe: origin + pixel, contribution + flags; direction and length
+//     are recomputed from the light): control words in shared memory (claim / commit cost a shared atomic, not an L2
+//     round trip -- a first version with ONE global queue serialised on its head counter: 3 us per claim, 411 ms per
+//     frame, profiles/r2a), data in global memory that never leaves L2 (9.7 MB for the whole grid, rewritten in place);
+//   * a probe is walked by the SM that shaded it, soon after: its walk starts in tree nodes that are still in L1;
 //   * pixels become final soon after their batch, roughly in item order: the streamed host rows work as with k_wf_fused;
 //   * both walks go through ONE copy of the traversal code (any-hit is a run-time flag), as in k_wf_fused.
-// Memory ordering: producers store their entries, __syncwarp, then the leader's atom.release.gpu on the chunk counter
-// (MEMBAR.ALL.GPU + RED, no L1 invalidation); a consumer's leader reads the counter with a relaxed strong load, claims
-// with a CAS, and the warp then reads the entries with ld.cg (L2) -- issued after the observation by control
-// dependence and the warp barrier.  (ld.acquire would add CCTL.IVALL: the whole L1, tree included, per claim.)
-__device__ __forceinline__ uint32_t ldRelaxed(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void addRelease(uint32_t* p, uint32_t n) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(n) : "memory");
-}
+// Ring safety: a warp takes primary work only when its CTA has no complete unclaimed chunk, so at most 31 + 4 x 32
+// entries are ever pending or being walked; the ring holds 256.  The append still checks that the slot it is about to
+// reuse has been released (never observed to wait).
+constexpr uint32_t kRingEntries = 256u, kRingChunks = kRingEntries / 32u;
+
+struct PersistCtl {
+  uint32_t tail;                 // entries reserved so far (monotonic)
+  uint32_t head;                 // chunks claimed so far (monotonic)
+  uint32_t producing;            // warps of the CTA between taking a primary batch and committing its probes
+  uint32_t noPrimary;            // warps of the CTA that have seen the global primary counter run out
+  uint32_t commit[kRingChunks];  // entries written into the chunk currently occupying the ring slot
+  uint32_t inUse[kRingChunks];   // the ring slot is being walked
+};
 
 template <int MIN_BLOCKS, int SH>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_constant__ WavefrontParams W) {
   YB_STACK(SH);
+  __shared__ PersistCtl ctl;
   const DeviceScene& sc = W.base.sc;
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t nWork = W.itemsPadded * W.samplesPerLaunch;
-  const uint32_t nBatches = nWork / 32u;
   constexpr uint32_t kNone = 0xFFFFFFFFu;
+  volatile PersistCtl* vc = &ctl;
+  if (threadIdx.x < sizeof(PersistCtl) / 4u) reinterpret_cast<uint32_t*>(&ctl)[threadIdx.x] = 0u;
+  __syncthreads();
+  float4* const ring0 = W.q0 + (size_t)blockIdx.x * kRingEntries;
+  float4* const ring2 = W.q2 + (size_t)blockIdx.x * kRingEntries;
   bool primaryLeft = true;
   uint32_t idle = 0;
   for (;;) {
     // ---- what this warp does next --------------------------------------------------------------------------------
-    uint32_t chunk = kNone, count = 0, base = kNone;
+    uint32_t chunk = kNone, count = 0, base = kNone, fin = 0;
     if (lane == 0) {
-      for (;;) {                                                   // (1) a committed chunk?
-        const uint32_t h = ldRelaxed(&W.work[1]);
-        const uint32_t c = ldRelaxed(&W.commit[h]);
+      for (;;) {                                                   // (1) a complete chunk of this CTA?
+        const uint32_t h = vc->head;
         uint32_t n = 0;
-        if (c == 32u) n = 32u;
-        else if (ldRelaxed(&W.work[5]) == nBatches) {              // every batch has committed: the queue length is final
-          const uint32_t t = ldRelaxed(&W.work[2]);
-          if (32u * h < t) { n = t - 32u * h < 32u ? t - 32u * h : 32u; if (ldRelaxed(&W.commit[h]) != n) n = 0; }
+        if (vc->commit[h & (kRingChunks - 1u)] == 32u) n = 32u;
+        else if (vc->noPrimary == 4u && vc->producing == 0u) {     // the CTA's queue is final: its last, partial chunk
+          const uint32_t t = vc->tail;
+          if (32u * h < t && vc->commit[h & (kRingChunks - 1u)] == t - 32u * h) n = t - 32u * h;
         }
         if (n == 0) break;
-        if (atomicCAS(&W.work[1], h, h + 1u) == h) { chunk = h; count = n; break; }
+        if (atomicCAS(&ctl.head, h, h + 1u) == h) {
+          chunk = h; count = n;
+          vc->inUse[h & (kRingChunks - 1u)] = 1u;
+          vc->commit[h & (kRingChunks - 1u)] = 0u;
+          break;
+        }
       }
-      if (chunk == kNone && primaryLeft) base = atomicAdd(&W.work[0], 32u);      // (2) a primary batch
+      if (chunk == kNone && primaryLeft) {                         // (2) a primary batch
+        atomicAdd(&ctl.producing, 1u);
+        base = atomicAdd(&W.work[0], 32u);
+        if (base >= nWork) { atomicSub(&ctl.producing, 1u); atomicAdd(&ctl.noPrimary, 1u); }
+      }
+      if (chunk == kNone && (base == kNone || base >= nWork))      // (3) nothing right now: is the CTA finished?
+        fin = (vc->noPrimary == 4u && vc->producing == 0u && 32u * vc->head >= vc->tail) ? 1u : 0u;
+      __threadfence_block();
     }
     chunk = __shfl_sync(kFull, chunk, 0);
     count = __shfl_sync(kFull, count, 0);
     base = __shfl_sync(kFull, base, 0);
     const bool anyPhase = chunk != kNone;
-    if (!anyPhase && (base == kNone || base >= nWork)) {           // (3) nothing to do right now
+    if (!anyPhase && (base == kNone || base >= nWork)) {
       primaryLeft = false;
-      uint32_t fin = 0;
-      if (lane == 0 && ldRelaxed(&W.work[5]) == nBatches) {
-        const uint32_t t = ldRelaxed(&W.work[2]);
-        fin = 32u * ldRelaxed(&W.work[1]) >= t ? 1u : 0u;
-      }
       if (__shfl_sync(kFull, fin, 0)) break;
       // (safety net, never reached in a correct run: ~3 s of idling ends the warp and raises work[6] instead of
       // hanging the device)
       if (++idle > (1u << 24)) { if (lane == 0) atomicExch(&W.work[6], 1u); break; }
-      __nanosleep(200);
+      __nanosleep(100);
       continue;
     }
     // ---- set up the walk: a probe of the chunk, or the camera ray of an item ----------------------------------------
@@ -795,11 +810,11 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
     bool busy = false, valid = false;
     int u = 0, v = 0;
     uint32_t sLocal = 0, item = 0, outIndex = 0;
-    const uint32_t entry = 32u * chunk + lane;
+    const uint32_t slot = (32u * chunk + lane) & (kRingEntries - 1u);
     if (anyPhase) {
       valid = lane < count;
       if (valid) {
-        const float4 a = __ldcg(&W.q0[entry]);
+        const float4 a = __ldcg(&ring0[slot]);
         outIndex = __float_as_uint(a.w);
         // illuminationAtPoint's probe (Lights.hs:20-24) from its origin: direction and length as shadeAndEmit computes them
         const V3 p0 = mk(a.x, a.y, a.z);
@@ -823,7 +838,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
       // ---- result of the probes: every pixel of the chunk is stored exactly once, here ------------------------------
       uint32_t row = 0;
       if (valid) {
-        const float4 c = __ldcg(&W.q2[entry]);
+        const float4 c = __ldcg(&ring2[slot]);
         const bool unoccluded = s.best == kNoHit;
         const uint32_t flags = __float_as_uint(c.w);
         const float qnan = __uint_as_float(0x7FFFFFFFu);
@@ -833,40 +848,50 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
         row = flags >> 3;
       }
       __syncwarp();
-      if (lane == 0) W.commit[chunk] = 0u;                         // clean for the next launch
-      if (W.discardQueue && count == 32u && lane < 8u) {           // 2 x 512 B = 8 lines of 128 B, read and done with
-        const char* line = (lane < 4u ? (const char*)(W.q0 + 32u * (size_t)chunk) : (const char*)(W.q2 + 32u * (size_t)chunk)) +
-                           128u * (lane & 3u);
-        asm volatile("discard.global.L2 [%0], 128;" :: "l"(line) : "memory");
-      }
+      if (lane == 0) { __threadfence_block(); vc->inUse[chunk & (kRingChunks - 1u)] = 0u; }     // the slot may be rewritten
       if (W.rowFlags) rowsSignal(W, row, valid, lane);
     } else {
-      // ---- shading; the probes of the batch go to the queue ----------------------------------------------------------
+      // ---- shading; the probes of the batch go to the CTA's ring -----------------------------------------------------
       LocalProbe pr;
       pr.emit = false; pr.nanBits = 0; pr.row = 0; pr.tMax = 0.0f;
       pr.origin = mk(0, 0, 0); pr.dir = mk(0, 0, 1); pr.contrib = mk(0, 0, 0);
       const uint32_t pixel = (uint32_t)(W.base.width * v + u);
       shadeAndEmit<false, true>(W, valid, item, pixel, v, r, s.tMax, s.best, lane, sLocal, &pr);
       const unsigned m = __ballot_sync(kFull, pr.emit);
-      if (m) {
-        const uint32_t n = (uint32_t)__popc(m);
-        uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&W.work[2], n);
-        first = __shfl_sync(kFull, first, 0);
-        if (pr.emit) {
-          const uint32_t e = first + (uint32_t)__popc(m & ((1u << lane) - 1u));
-          __stcg(&W.q0[e], make_float4(pr.origin.x, pr.origin.y, pr.origin.z, __uint_as_float(sLocal * W.framePixels + pixel)));
-          __stcg(&W.q2[e], make_float4(pr.contrib.x, pr.contrib.y, pr.contrib.z, __uint_as_float(pr.nanBits | (pr.row << 3))));
-        }
-        __syncwarp();
-        if (lane == 0) {                                           // commit: the append touches one or two chunks
-          const uint32_t c0 = first >> 5, inFirst = 32u - (first & 31u);
-          if (n <= inFirst) addRelease(&W.commit[c0], n);
-          else { addRelease(&W.commit[c0], inFirst); addRelease(&W.commit[c0 + 1u], n - inFirst); }
+      const uint32_t n = (uint32_t)__popc(m);
+      uint32_t first = 0;
+      if (lane == 0 && n) {
+        first = atomicAdd(&ctl.tail, n);
+        // the ring slots about to be written must have been released: chunk k reuses the slot of chunk k - 8
+        const uint32_t lastChunk = (first + n - 1u) >> 5;
+        uint32_t spins = 0;
+        while ((lastChunk >= kRingChunks && vc->head + kRingChunks <= lastChunk) ||
+               vc->inUse[lastChunk & (kRingChunks - 1u)] || vc->inUse[(first >> 5) & (kRingChunks - 1u)]) {
+          if (vc->head > lastChunk) break;                         // (cannot happen: our chunk is not committed yet)
+          if (++spins > (1u << 24)) { atomicExch(&W.work[6], 2u); break; }
+          __nanosleep(50);
         }
       }
+      first = __shfl_sync(kFull, first, 0);
+      if (pr.emit) {
+        const uint32_t e = (first + (uint32_t)__popc(m & ((1u << lane) - 1u))) & (kRingEntries - 1u);
+        __stcg(&ring0[e], make_float4(pr.origin.x, pr.origin.y, pr.origin.z, __uint_as_float(sLocal * W.framePixels + pixel)));
+        __stcg(&ring2[e], make_float4(pr.contrib.x, pr.contrib.y, pr.contrib.z, __uint_as_float(pr.nanBits | (pr.row << 3))));
+      }
       __syncwarp();
-      if (lane == 0) addRelease(&W.work[5], 1u);                   // after the commits, in program order
+      if (lane == 0) {                                             // commit: the append touches one or two chunks
+        __threadfence_block();
+        if (n) {
+          const uint32_t c0 = first >> 5, inFirst = 32u - (first & 31u);
+          if (n <= inFirst) atomicAdd(&ctl.commit[c0 & (kRingChunks - 1u)], n);
+          else {
+            atomicAdd(&ctl.commit[c0 & (kRingChunks - 1u)], inFirst);
+            atomicAdd(&ctl.commit[(c0 + 1u) & (kRingChunks - 1u)], n - inFirst);
+          }
+        }
+        __threadfence_block();
+        atomicSub(&ctl.producing, 1u);
+      }
       if (W.rowFlags) rowsSignal(W, pr.row, valid && !pr.emit, lane);            // final without a probe
     }
   }
@@ -1209,12 +1234,13 @@ __global__ void k_wf_count(const __grid_constant__ WavefrontParams W) {
 // Persistent launch: exactly as many 128-thread CTAs as can be resident (occupancy API), so that every
 // CTA is scheduled in the first wave and pulls work until the queue is empty.
 static void launchPersistent(void (*kernel)(WavefrontParams), const WavefrontParams& W, int numSMs,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int maxPerSM = 255) {
   // (asking for the smallest shared-memory carve-out instead of the driver's default 32 KB: primary unchanged, shadow
   // kernel 0.426 -> 0.453 ms; not done.  profiles/r1ab section 7)
   int perSM = 0;
   if (W.blocksPerSM) perSM = (int)W.blocksPerSM;
   else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 128, 0) != cudaSuccess || perSM < 1) perSM = 8;
+  if (perSM > maxPerSM) perSM = maxPerSM;
   kernel<<<numSMs * perSM, 128, 0, stream>>>(W);
 }
 
@@ -1265,7 +1291,8 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
 #endif
     const bool oneSlot = wide && !area && !W.dense;
     if (oneSlot && W.persist) {
-      launchPersistent(YB_PICK_SH(sh, (k_wf_persist<8, 0>), (k_wf_persist<8, 8>), (k_wf_persist<8, 12>)), W, numSMs, stream);
+      launchPersistent(YB_PICK_SH(sh, (k_wf_persist<8, 0>), (k_wf_persist<8, 8>), (k_wf_persist<8, 12>)), W, numSMs, stream,
+                       16);                                         // the rings in q0 / q2 are sized for 16 CTAs per SM
       singleKernelEvents();
       tail();
       continue;

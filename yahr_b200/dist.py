@@ -7,12 +7,15 @@ The only exchange is at the end of a frame -- the reference's `concat` of per-ti
 
   "p2p"    tile i -> rank i mod G; rank 0's frame buffer is mapped into every rank through CUDA IPC and
            the render kernel stores each finished pixel straight into it over NVLink: the gather
-           is fused into the kernel's epilogue and overlaps traversal.  A one-element NCCL
-           all-reduce on the render stream is the completion fence.
+           is fused into the kernel's epilogue and overlaps traversal.
   "rows"   the frame is cut into whole rows of the reference's tile grid, row r -> rank r mod G; every rank renders
-           its rows into a local frame and pushes them into rank 0's frame (same IPC mapping) with a few large
-           device-to-device copies (one strided 2-D copy when the rows are equally tall) on the render stream, then
-           the same fence.  The copies run after the kernels instead of under them, but they are bulk transfers.
+           its rows into a local frame with ONE persistent kernel that publishes finished tile rows, and each
+           finished row is copied into rank 0's frame (same IPC mapping) by the copy engine over NVLink while the
+           rest of the share is traced (yahr_b200_render_device_shard, streamed push): bulk transfers that overlap
+           the rendering.
+  Both end with the flag fence (yahr_b200_flag_signal / yahr_b200_flags_wait): a sequence number per rank in rank 0's
+  memory that rank 0's stream waits for -- no collective on the frame path (round 1 used a one-element NCCL
+  all-reduce; fence="nccl" keeps it).
   "auto"   (default) "p2p" up to 5 GPUs, "rows" from 6 (C4: 4 GPUs p2p 0.64 / rows 0.74 ms, 8 GPUs 0.65 / 0.49 ms).
   "reduce" every rank renders into a zeroed local full frame and the frames are summed onto rank 0
            with one NCCL reduce -- exact, because every pixel has exactly one owner and x + 0 = x.
@@ -27,7 +30,7 @@ from . import api
 
 
 class TileShardedRenderer:
-    def __init__(self, scene, cam, mode="auto", want_primid=False, group=None):
+    def __init__(self, scene, cam, mode="auto", want_primid=False, group=None, fence="flags"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -54,7 +57,7 @@ class TileShardedRenderer:
         self.primid = None
         self._peer_rgb = None     # "p2p": rank 0's frame as seen from this rank
         self._peer_pid = None
-        self._peer_base_rgb = self._peer_base_pid = None
+        self._opened_blocks = []
         self._fence = torch.zeros(1, dtype=torch.float32, device=dev)
         if self.mode in ("local", "reduce") or self.rank == 0:
             self.frame = torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -65,37 +68,49 @@ class TileShardedRenderer:
             self.local = torch.zeros(shape, dtype=torch.float32, device=dev)
             if want_primid:
                 self.local_pid = torch.zeros((self.height, self.width), dtype=torch.int32, device=dev)
+        # End-of-frame fence.  "flags": every pushing rank stores the frame's sequence number into its word of a small
+        # array in rank 0's memory once its rows have landed, and rank 0's stream waits for the words
+        # (yahr_b200_flag_signal / yahr_b200_flags_wait: no collective, no host round trip).  "nccl": round 1's
+        # one-element all-reduce on the render stream.
+        self.fence = fence
+        self._seq = 0
+        self._flags = None          # rank 0: the flag words (one per rank)
+        self._peer_flag = None      # other ranks: device pointer of this rank's word in rank 0's array
+        self._peer_base_flags = None
         if self.mode in ("p2p", "rows"):
             handles = [None]
             if self.rank == 0:
                 L = api.lib()
                 import ctypes as C
-                hb = C.create_string_buffer(64)
-                api._check(L.yahr_b200_ipc_export(C.c_void_p(self.frame.data_ptr()), hb))
-                hp = None
-                if want_primid:
-                    hp_b = C.create_string_buffer(64)
-                    api._check(L.yahr_b200_ipc_export(C.c_void_p(self.primid.data_ptr()), hp_b))
-                    hp = hp_b.raw
+
+                def export(t):
+                    b = C.create_string_buffer(64)
+                    api._check(L.yahr_b200_ipc_export(C.c_void_p(t.data_ptr()), b))
+                    return b.raw
+                # its own cudaMalloc block (>= 1 MB requests are never packed with other tensors by torch's allocator)
+                self._flags = torch.zeros(1 << 18, dtype=torch.int32, device=dev)
                 # torch's caching allocator sub-allocates: ship the offset inside the IPC block too
-                handles = [(hb.raw, hp, self._alloc_offset(self.frame), self._alloc_offset(self.primid))]
+                handles = [(export(self.frame), export(self.primid) if want_primid else None,
+                            self._alloc_offset(self.frame), self._alloc_offset(self.primid),
+                            export(self._flags), self._alloc_offset(self._flags))]
             dist.broadcast_object_list(handles, src=0, group=group)
             if self.rank != 0:
                 import ctypes as C
                 L = api.lib()
-                hb, hp, off_rgb, off_pid = handles[0]
-                p = C.c_void_p()
-                api._check(L.yahr_b200_ipc_open(hb, C.byref(p)))
-                self._peer_base_rgb = p.value
-                self._peer_rgb = p.value + off_rgb
+                hb, hp, off_rgb, off_pid, hf, off_flags = handles[0]
+                opened = {}
+
+                def open_block(h):
+                    if h not in opened:
+                        p = C.c_void_p()
+                        api._check(L.yahr_b200_ipc_open(h, C.byref(p)))
+                        opened[h] = p.value
+                    return opened[h]
+                self._peer_rgb = open_block(hb) + off_rgb
                 if hp is not None:
-                    q = C.c_void_p()
-                    if hp == hb:
-                        q = p
-                    else:
-                        api._check(L.yahr_b200_ipc_open(hp, C.byref(q)))
-                        self._peer_base_pid = q.value          # a mapping of its own: closed in close()
-                    self._peer_pid = q.value + off_pid
+                    self._peer_pid = open_block(hp) + off_pid
+                self._peer_flag = open_block(hf) + off_flags + 4 * self.rank
+                self._opened_blocks = list(opened.values())
             dist.barrier(group=group)
         torch.cuda.synchronize()
         # scene_ms: BVH build + upload through the C ABI; exchange_ms: frame buffers, IPC handles, handshake
@@ -151,7 +166,7 @@ class TileShardedRenderer:
                 api.render_device_shard(self.scene, self.cam, self.rank, self.world, self.local.data_ptr(), self._peer_rgb,
                                         self.local_pid.data_ptr() if self.local_pid is not None else None,
                                         self._peer_pid, **kw)
-            dist.all_reduce(self._fence, group=self.group)      # completion fence on the render stream
+            self._end_of_frame(stream)
             return
         kw.update(tile_stride=self.world, tile_offset=self.rank)
         if self.mode == "p2p":
@@ -160,7 +175,7 @@ class TileShardedRenderer:
             else:
                 rgb, pid = self._peer_rgb, self._peer_pid
             self.scene.render_device(self.cam, rgb, pid, **kw)
-            dist.all_reduce(self._fence, group=self.group)      # completion fence on the render stream
+            self._end_of_frame(stream)
         elif self.mode == "reduce":
             self.frame.zero_()
             if self.primid is not None:
@@ -173,6 +188,22 @@ class TileShardedRenderer:
         else:
             raise ValueError("unknown mode " + self.mode)
 
+    def _end_of_frame(self, stream):
+        """Completion fence on the render stream: rank 0's stream does not pass it before every rank's rows are in."""
+        if self.fence == "nccl":
+            self.dist.all_reduce(self._fence, group=self.group)
+            return
+        import ctypes as C
+        L = api.lib()
+        self._seq += 1
+        if self.rank == 0:
+            L.yahr_b200_flags_wait.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+            api._check(L.yahr_b200_flags_wait(C.c_void_p(self._flags.data_ptr()), 1, self.world - 1,
+                                              C.c_uint32(self._seq), C.c_void_p(stream)))
+        else:
+            L.yahr_b200_flag_signal.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+            api._check(L.yahr_b200_flag_signal(C.c_void_p(self._peer_flag), C.c_uint32(self._seq), C.c_void_p(stream)))
+
     def stats_render(self, **kw):
         """One synchronous local render of this rank's tiles into a scratch frame, returning the
         library's stats (ray counts, kernel ms)."""
@@ -184,12 +215,13 @@ class TileShardedRenderer:
         return st
 
     def close(self):
-        if self._peer_rgb is not None:
+        if self._opened_blocks:
             import ctypes as C
-            api.lib().yahr_b200_ipc_close(C.c_void_p(self._peer_base_rgb))
-            if self._peer_base_pid is not None:
-                api.lib().yahr_b200_ipc_close(C.c_void_p(self._peer_base_pid))
-            self._peer_rgb = self._peer_pid = self._peer_base_pid = None
+            self.torch.cuda.synchronize()
+            for base in self._opened_blocks:             # every IPC mapping this rank opened (frame, IDs, flags)
+                api.lib().yahr_b200_ipc_close(C.c_void_p(base))
+            self._opened_blocks = []
+            self._peer_rgb = self._peer_pid = self._peer_flag = None
         self.scene.close()
 
 
