@@ -358,13 +358,13 @@ def test_streamed_rows_equal_the_banded_copies_and_the_device_frame(monkeypatch)
         b_rgb, b_pid, b_st = s.render(cam)
         monkeypatch.delenv("YAHR_B200_HOST_STREAM")
         monkeypatch.setenv("YAHR_B200_HOST_STREAM", "1")
-        for fused in ("0", "1", "3"):             # streamed rows with the two-kernel set / the fused kernel (both builds)
+        for fused in ("0", "1", "2", "3"):        # streamed rows with the two-kernel set / k_wf_fused (both builds) / k_wf_persist
             monkeypatch.setenv("YAHR_B200_HOST_FUSED", fused)
             t_rgb, t_pid, _ = s.render(cam)
             assert np.array_equal(t_rgb.view(np.uint32), ref.view(np.uint32)) and np.array_equal(t_pid, rpid)
         monkeypatch.delenv("YAHR_B200_HOST_FUSED")
         monkeypatch.delenv("YAHR_B200_HOST_STREAM")
-        for tune in (0x1000, 0x3000):     # fused kernel on the device-resident frame
+        for tune in (0x1000, 0x3000, 0x8000, 0x8200):     # k_wf_fused / k_wf_persist on the device-resident frame
             fdev = torch.full((h, w, 3), float("nan"), dtype=torch.float32, device="cuda")
             s.render_device(cam, fdev.data_ptr(), None, tune=tune)
             assert torch.equal(fdev.view(torch.int32), dev.view(torch.int32))

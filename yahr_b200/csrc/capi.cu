@@ -355,7 +355,11 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
       CU(cudaMemset(sc->wfWork, 0, 16 * sizeof(uint32_t)));
     }
     W.base = P;
-    W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = nL > 1 ? 1u : 0u;
+    // light slots: 1 -> compacted queue, every pixel stored once; 2 -> compacted queue + float atomics (order-free for
+    // two addends; YAHR_B200_NO_TWO_SLOT=1 keeps the dense path); 3 or more -> dense entries + in-order resolve
+    static const bool noTwoSlot = getenv("YAHR_B200_NO_TWO_SLOT") != nullptr;
+    W.twoSlot = (nL == 2 && !noTwoSlot) ? 1u : 0u;
+    W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = (nL > 1 && !W.twoSlot) ? 1u : 0u;
     W.itemPixels = ts.d_itemPixels;
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
     static const uint32_t envTune = getenv("YAHR_B200_TUNE") ? (uint32_t)strtoul(getenv("YAHR_B200_TUNE"), nullptr, 0) : 0u;
@@ -405,7 +409,7 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
       sc->wfEntries[slot] = entries;
     }
     W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot];
-    W.visibility = plan.entriesPerItem > 1 ? sc->wfVis[slot] : nullptr;
+    W.visibility = W.dense ? sc->wfVis[slot] : nullptr;
     W.work = sc->wfWork + 8 * slot;
     W.bandStat = bandStat;
     W.base.tiles = ts.d_tiles + first; W.base.nTiles = count;
@@ -893,7 +897,7 @@ int yahr_b200_render_device_shard(yahr_scene* scene, const yahr_camera* cam, con
         if (prc) return prc;
         const TileSet& pts = *plan.ts;
         const bool pushPid0 = d_primid_gather && d_primid_local && d_primid_gather != d_primid_local;
-        if (plan.wavefront && !plan.W.dense && pts.rowY.size() >= 2 && pts.d_rowOfV && scene->dev.wide &&
+        if (plan.wavefront && !plan.W.dense && !plan.W.twoSlot && pts.rowY.size() >= 2 && pts.d_rowOfV && scene->dev.wide &&
             scene->dev.nAreaLights == 0 && plan.W.wideTree && o.traversal == YAHR_TRAVERSAL_REFERENCE) {
           for (auto& s2 : scene->renderStream) if (!s2) CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
           if (!scene->copyStream) CU(cudaStreamCreateWithFlags(&scene->copyStream, cudaStreamNonBlocking));
@@ -1004,9 +1008,14 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
   plan.W.rgb8 = rgb8_out ? scene->d_rgb8 : nullptr;
   // rows complete in item order only when every batch is final at once: the fused kernel (with the two-kernel set
   // every lit row completes in the shadow phase, after the whole primary trace)
-  // (k_wf_persist by default; YAHR_B200_HOST_FUSED=1 / 2 selects round 1's per-batch kernel k_wf_fused, 0 the two-kernel set)
-  if (const char* f = getenv("YAHR_B200_HOST_FUSED")) { plan.W.fused = (uint32_t)atoi(f) & 3u; plan.W.persist = 0u; }
-  else if (plan.P.depth == 1) plan.W.persist = 1u;
+  // k_wf_fused by default (C4 1.59 ms against 1.75 - 1.90 for k_wf_persist on a whole frame, profiles/r2c-r2e);
+  // YAHR_B200_HOST_FUSED=3 selects k_wf_persist, 2 the 72-register build of k_wf_fused, 0 the two-kernel set
+  {
+    const char* f = getenv("YAHR_B200_HOST_FUSED");
+    const uint32_t k = f ? (uint32_t)atoi(f) & 3u : 1u;
+    plan.W.persist = (k == 3u && plan.P.depth == 1) ? 1u : 0u;
+    plan.W.fused = k == 3u ? 1u : k;
+  }
   uint32_t launches = 0;
   CU(cudaMemsetAsync(scene->d_rowDone, 0, nRowsS * sizeof(uint32_t), rs));
   CU(cudaMemsetAsync(scene->d_counters, 0, 3 * sizeof(unsigned long long), rs));
@@ -1173,7 +1182,7 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
     {
       const char* env = getenv("YAHR_B200_HOST_STREAM");
       const uint32_t nRowsS = (uint32_t)ts.rowY.size();
-      bool useStream = plan.wavefront && !plan.W.dense && spp == 1 && nRowsS >= 2 && ts.d_rowOfV;
+      bool useStream = plan.wavefront && !plan.W.dense && !plan.W.twoSlot && spp == 1 && nRowsS >= 2 && ts.d_rowOfV;
       // the 8-bit frame is written by the per-batch kernels only (k_wf_fused*: 4-wide tree, no area lights)
       if (rgb8_out && !(scene->dev.wide && scene->dev.nAreaLights == 0 && !getenv("YAHR_B200_HOST_FUSED"))) useStream = false;
       if (useStream && env) useStream = atoi(env) != 0;

@@ -79,7 +79,10 @@ struct WavefrontParams {
   uint32_t samplesPerLaunch;  // spp > 1: one launch traces this many samples of every pixel (work = sample-major)
   uint32_t itemsPadded;       // nItems rounded up to a multiple of 32: work items per sample
   uint32_t framePixels;       // width * height: pixels between the per-sample frames of sampleOut
-  uint32_t dense;             // several lights: shadow slots entry = item * nLights + light
+  uint32_t dense;             // three or more light slots: shadow entry = item * nSlots + slot, k_wf_resolve sums in slot order
+  uint32_t twoSlot;           // exactly two light slots: compacted queue; the pixel gets its base value from the shading
+                              // step and every unoccluded probe ADDS its contribution with a float atomic -- with two
+                              // addends on top of +0 the sum does not depend on their order ((0 + a) + b = (0 + b) + a)
   uint32_t leafThreshold;     // leaf parking: run the leaf code once this many lanes hold a leaf
   uint32_t blocksPerSM;       // tuning: persistent CTAs per SM (0 = as many as fit)
   uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)

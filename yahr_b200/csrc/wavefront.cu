@@ -339,7 +339,8 @@ __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& 
 
 template <bool ANY_HIT, class STK>
 __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool busy,
-                                                 int leafThreshold, bool leafRun, bool anyRt = false) {
+                                                 int leafThreshold, bool leafRun, bool anyRt = false,
+                                                 bool octants = true) {
   const bool nanLane = busy && r.exactNaN;
   bool run = busy && !r.exactNaN;
   const unsigned mRun = __ballot_sync(kFull, run);
@@ -347,7 +348,10 @@ __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ra
     int oct = -1;
     const int mine = rayOctant(r);
     const int lead = __shfl_sync(kFull, mine, __ffs(mRun) - 1);
-    if (__all_sync(kFull, !run || mine == lead)) oct = lead;
+    // octants = false: every warp runs the ONE generic inner loop (min / max per lane): ~6 % more instructions per
+    // step, but the kernels that mix closest-hit and any-hit walks of different octants on one SM (k_wf_persist) keep a
+    // much smaller set of hot instructions (the L1.5 instruction cache holds 32 KB)
+    if (octants && __all_sync(kFull, !run || mine == lead)) oct = lead;
     const RayPack rp = packRay(r);
     for (;;) {
       switch (oct) {
@@ -516,7 +520,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       // several slots: the base is stored now and k_wf_resolve adds to it.  One slot: every pixel is stored exactly
       // ONCE -- here (below) when no probe is emitted, else by the shadow kernel -- so the frame may live in a
       // peer GPU or in mapped host memory without any traffic beyond the frame itself.
-      if (W.dense) { out[0] = base.x; out[1] = base.y; out[2] = base.z; }
+      if (W.dense || W.twoSlot) { out[0] = base.x; out[1] = base.y; out[2] = base.z; }
     }
   }
   // one probe per light SLOT with lensq k > 0 (point lights, then every sample of every area light -- the
@@ -580,7 +584,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       for (uint32_t j = 0; j < l.samples; ++j, ++slot) doSlot(slot, areaLightPoint(l, ctx, slot), l.flux, true, l.normal);
     }
   }
-  if (hit && !W.dense && nEmit == 0u) {
+  if (hit && !W.dense && !W.twoSlot && nEmit == 0u) {
     const float qnan = __uint_as_float(0x7FFFFFFFu);
     const size_t index = (size_t)(sLocal * W.framePixels + pixel);
     const float x = (nanBits & 1u) ? qnan : 0.0f, y = (nanBits & 2u) ? qnan : 0.0f, z = (nanBits & 4u) ? qnan : 0.0f;
@@ -599,6 +603,17 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
 // host memory.  Several slots: only the visibility flag is recorded.
 __device__ __forceinline__ uint32_t shadowResult(const WavefrontParams& W, uint32_t entry, bool unoccluded) {
   if (W.visibility) { W.visibility[entry] = unoccluded ? 1 : 0; return 0u; }
+  if (W.twoSlot) {
+    // two light slots: sum = foldl (+) 0 over the visible ones (Integrators.hs:50-61) on top of the base value the
+    // shading step stored; (0 + a) + b and (0 + b) + a are the same float, so the two probes of a pixel may land in
+    // either order
+    if (unoccluded) {
+      const float4 c = W.q2[entry];
+      float* out = W.sampleOut + 3 * (size_t)__float_as_uint(W.q1[entry].w);
+      atomicAdd(out + 0, c.x); atomicAdd(out + 1, c.y); atomicAdd(out + 2, c.z);
+    }
+    return 0u;
+  }
   const float4 b = W.q1[entry];
   float4 c = make_float4(0.0f, 0.0f, 0.0f, W.q2[entry].w);
   if (unoccluded) c = W.q2[entry];
@@ -749,6 +764,7 @@ template <int MIN_BLOCKS, int SH>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_constant__ WavefrontParams W) {
   YB_STACK(SH);
   __shared__ PersistCtl ctl;
+  __shared__ float4 stash[128];          // per lane: contribution + flags of the probe being walked
   const DeviceScene& sc = W.base.sc;
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t nWork = W.itemsPadded * W.samplesPerLaunch;
@@ -813,8 +829,17 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
     const uint32_t slot = (32u * chunk + lane) & (kRingEntries - 1u);
     if (anyPhase) {
       valid = lane < count;
+      float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (valid) {
-        const float4 a = __ldcg(&ring0[slot]);
+        a = __ldcg(&ring0[slot]);
+        stash[threadIdx.x] = __ldcg(&ring2[slot]);
+      }
+      // The ring slot is released as soon as its 32 entries have been READ (the ballot consumes the loaded words, the
+      // shared store the other record), not when the walks end: walk times are heavy-tailed, and a slot pinned by one
+      // long chunk stalled the CTA's three other warps at the ring's wrap-around (first version: C4 1.89 ms, r2b).
+      __ballot_sync(kFull, __float_as_uint(a.w) == 0xFFFFFFFFu);
+      if (lane == 0) { __threadfence_block(); vc->inUse[chunk & (kRingChunks - 1u)] = 0u; }
+      if (valid) {
         outIndex = __float_as_uint(a.w);
         // illuminationAtPoint's probe (Lights.hs:20-24) from its origin: direction and length as shadeAndEmit computes them
         const V3 p0 = mk(a.x, a.y, a.z);
@@ -832,13 +857,13 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
         busy = travBegin(sc, r, 1e6f, s);
       }
     }
-    traverseWarpWide<false>(sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, anyPhase);
+    traverseWarpWide<false>(sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0, anyPhase, W.packed != 0);
     flushCounts(W, s, anyPhase ? 1 : 0, !anyPhase && valid && s.best != kNoHit);
     if (anyPhase) {
       // ---- result of the probes: every pixel of the chunk is stored exactly once, here ------------------------------
       uint32_t row = 0;
       if (valid) {
-        const float4 c = __ldcg(&ring2[slot]);
+        const float4 c = stash[threadIdx.x];
         const bool unoccluded = s.best == kNoHit;
         const uint32_t flags = __float_as_uint(c.w);
         const float qnan = __uint_as_float(0x7FFFFFFFu);
@@ -847,8 +872,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
                    (flags & 4u) ? qnan : 0.0f + (unoccluded ? c.z : 0.0f));
         row = flags >> 3;
       }
-      __syncwarp();
-      if (lane == 0) { __threadfence_block(); vc->inUse[chunk & (kRingChunks - 1u)] = 0u; }     // the slot may be rewritten
       if (W.rowFlags) rowsSignal(W, row, valid, lane);
     } else {
       // ---- shading; the probes of the batch go to the CTA's ring -----------------------------------------------------
@@ -1289,7 +1312,7 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
       continue;
     }
 #endif
-    const bool oneSlot = wide && !area && !W.dense;
+    const bool oneSlot = wide && !area && !W.dense && W.base.sc.nSlots <= 1u;
     if (oneSlot && W.persist) {
       launchPersistent(YB_PICK_SH(sh, (k_wf_persist<8, 0>), (k_wf_persist<8, 8>), (k_wf_persist<8, 12>)), W, numSMs, stream,
                        16);                                         // the rings in q0 / q2 are sized for 16 CTAs per SM
