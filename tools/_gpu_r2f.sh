@@ -7,7 +7,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 done
 YAHR_B200_SHARD_STREAM=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --exchange rows --no-extra > gpurun_out/r2f_bench_n2_rows_nostream.json 2> gpurun_out/r2f_bench_n2_rows_nostream.err
 timeout 600 python tools/sweep_r2.py --workloads c2-area --tunes 0 --shares 1 --spp 16 > gpurun_out/r2f_two_slot.txt 2>&1
-YAHR_B200_NO_TWO_SLOT=1 timeout 600 python tools/sweep_r2.py --workloads c2-area --tunes 0 --shares 1 --spp 16 >> gpurun_out/r2f_two_slot.txt 2>&1
+YAHR_B200_TWO_SLOT=0 timeout 600 python tools/sweep_r2.py --workloads c2-area --tunes 0 --shares 1 --spp 16 >> gpurun_out/r2f_two_slot.txt 2>&1
 timeout 600 python tools/sweep_r2.py --workloads c5-area --tunes 0 --shares 1 --spp 16 --reps 2 >> gpurun_out/r2f_two_slot.txt 2>&1
-YAHR_B200_NO_TWO_SLOT=1 timeout 600 python tools/sweep_r2.py --workloads c5-area --tunes 0 --shares 1 --spp 16 --reps 2 >> gpurun_out/r2f_two_slot.txt 2>&1
+YAHR_B200_TWO_SLOT=0 timeout 600 python tools/sweep_r2.py --workloads c5-area --tunes 0 --shares 1 --spp 16 --reps 2 >> gpurun_out/r2f_two_slot.txt 2>&1
 cat gpurun_out/r2f_two_slot.txt
