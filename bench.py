@@ -9,7 +9,7 @@ reference's integrator needs (Integrators.hs:59).  Metric: Mrays/s (primary + sh
   e2e   : the same frame through the host-buffer C-ABI call (yahr_b200_render): kernel parameters
           up, frame down to pinned host memory, inside the timed region
 The reference arm (--impl reference) times the CPU oracle port of the reference's render loop,
-tiles as OpenMP tasks on all host cores (the GHC reference cannot be built in this image).
+tiles dealt to one std::thread per host core (the GHC reference cannot be built in this image).
 """
 import argparse
 import json
@@ -204,7 +204,7 @@ def cpu_baseline_run(sc, cam, target_seconds=15.0, threads=0, steps=1, warmup=0)
     bpr, rays, _ = ob.bytes_per_ray(last)
     v = float(np.mean([x[0] for x in vals]))
     sample = ("%d of %d reference tiles (every %dth, %d rays) of the same frame; oracle C++ port of the reference, "
-              "tiles as OpenMP dynamic tasks (renderPar analogue); BVH build %.1f s excluded"
+              "tiles pulled by one std::thread per core from a shared counter (renderPar analogue); BVH build %.1f s excluded"
               % (last["tiles"], n_tiles, stride, rays, build_s))
     d = {"value": v, "unit": UNIT, "cores": int(last["threads"]), "kind": "port", "sample": sample,
          "seconds_per_step": float(np.mean([x[1] for x in vals])), "bytes_per_ray_sample": bpr,

@@ -48,7 +48,7 @@ typedef struct {
 typedef struct {
   uint64_t n_node, n_tri, n_tricand, n_sph, n_shade, n_light, n_primary, n_shadow, n_secondary;
   double seconds;       // wall time of the pixel loop
-  int32_t threads;      // OpenMP threads used
+  int32_t threads;      // host threads used
   int32_t tiles;        // tiles rendered by this call
 } yo_stats;
 

@@ -410,7 +410,7 @@ def _render_device_counted(self, cam, d_rgb, d_primid=None, recursion_depth=1, s
     # per primitive test, 48 B per normal fetch, 8 B per stack push / pop; per shaded hit the surface (48 + 48 B),
     # material (32 B) and light (32 B); per probe its queue record written and read; per primary ray the pixel-table
     # entry (4 B) and the pixel (12 B)
-    probe_bytes = 2 * 32 if s_["launches"] <= 3 else 2 * 48
+    probe_bytes = 2 * 32 if s_["launches"] <= 2 else 2 * 48      # k_wf_persist ring record / two-kernel queue record
     b = (128 * tot["wide_nodes"] + 64 * tot["binary_nodes"] + 48 * tot["prim_tests"] + 48 * tot["normal_fetches"]
          + 8 * (tot["stack_pushes"] + tot["stack_pops"]) + 160 * tot["shaded"] + probe_bytes * s_["n_shadow"]
          + 16 * s_["n_primary"])
