@@ -167,6 +167,13 @@ int yahr_b200_scene_download_bvh(const yahr_scene* scene, uint32_t* order_out, f
  * floats; layout in csrc/device_types.cuh). */
 int yahr_b200_scene_download_wide(const yahr_scene* scene, float* wide_out);
 
+/* Inspection: the COMPRESSED copy of the wide nodes (n_wide_nodes x 16 words: origin' xyz + step exponents, 24 grid
+ * bytes + 8 spare, four child refs; csrc/wide_bvh.cu) and the exact boxes the compressed walk tests at the leaves
+ * (n_primitives x 8 floats by DFS position, n_multi_leaves x 8 floats: lo.xyz hi.x | hi.yz - -).  Any pointer may be
+ * NULL.  Error when the scene has no compressed nodes (non-finite box coordinates, or no wide tree). */
+int yahr_b200_scene_download_compressed(const yahr_scene* scene, float* cwide_out, float* leaf_box_out,
+                                        float* multi_box_out);
+
 /* --- render: replaces render / renderEval / renderPar + samplesToImage (main.hs:68-107) -------- */
 /* Host-buffer entry (the call the Haskell host makes).  rgb_out: W*H*3 floats, row-major, RGB
  * interleaved, row 0 = top -- exactly JuicyPixels' `Image PixelRGBF` storage (main.hs:98-107).

@@ -63,6 +63,12 @@ def gpu_render_modes(sc, cam, depth=1, spp=1, seed=0):
         st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
                               stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x400)
         outs["wavefront/binary"] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
+        # tuning bit 30: the wavefront set on the COMPRESSED wide nodes (conservative inner boxes, exact leaf boxes)
+        d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
+        d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
+        st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
+                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x40000000)
+        outs["wavefront/compressed"] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
     outs["reference"] = outs["mega/reference"]
     outs["ordered"] = outs["mega/ordered"]
     outs["info"] = s.info()
@@ -114,12 +120,16 @@ def test_parity_small_scenes(name):
     orgb, opid, _, ost = o.render(cam)
     o.close()
     outs = gpu_render_modes(sc, cam)
-    for mode in ("host", "mega/reference", "wavefront/reference", "wavefront/binary"):
+    for mode in ("host", "mega/reference", "wavefront/reference", "wavefront/binary", "wavefront/compressed"):
         rgb, pid, st = outs[mode]
         compare(rgb, pid, orgb, opid, 1.0, "%s/%s" % (name, mode))
         assert st["n_primary"] == ost["n_primary"]
         assert st["n_shadow"] == ost["n_shadow"], "shadow-ray count differs from Integrators.hs:59 semantics"
         assert st["launches"] >= 1
+    # the compressed walk visits a superset of inner nodes and the same leaves: frames and ray counts bit-identical
+    a, b = outs["wavefront/reference"], outs["wavefront/compressed"]
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
+    assert a[2]["n_shadow"] == b[2]["n_shadow"]
     for mode in ("mega/ordered", "wavefront/ordered"):
         rgb, pid, st = outs[mode]
         compare(rgb, pid, orgb, opid, 0.9999, name + "/" + mode)
@@ -201,6 +211,62 @@ def test_wide_tree_is_a_collapse_of_the_reference_tree(name):
     assert set(bbox) == set(wbox)
     for r in bbox:
         assert tuple(map(float, bbox[r])) == tuple(map(float, wbox[r]))
+
+
+def _decode_compressed(cw):
+    """Child boxes of the compressed wide nodes, decoded with the kernels' own arithmetic in binary32:
+    fma(2^23 + q, 2^e, origin') -- exact by construction (csrc/wide_bvh.cu)."""
+    org = cw[:, 0:3].view(np.float32)
+    eb = cw[:, 3]
+    step = np.stack([((eb >> (8 * d)) & 0xFF).astype(np.uint32) << 23 for d in range(3)], axis=1).view(np.float32)
+    words = {"lo": cw[:, 4:7], "hi": np.stack([cw[:, 7], cw[:, 8], cw[:, 9]], axis=1)}
+    out = {}
+    for side in ("lo", "hi"):
+        box = np.zeros((len(cw), 4, 3), np.float64)
+        for k in range(4):
+            q = ((words[side] >> (8 * k)) & 0xFF).astype(np.uint32)
+            f23 = (q | 0x4B000000).view(np.float32).astype(np.float64)           # 2^23 + q
+            exact = f23 * step.astype(np.float64) + org.astype(np.float64)       # exact in binary64
+            assert np.array_equal(exact.astype(np.float32).astype(np.float64), exact), "decoded coordinate not a float"
+            box[:, k, :] = exact
+        out[side] = box
+    return out["lo"], out["hi"]
+
+
+@pytest.mark.parametrize("name", ["terrain", "grid-sah", "bunny-depth6", "soup", "c1", "adversarial"])
+def test_compressed_nodes_contain_the_exact_boxes_and_leaf_boxes_are_exact(name):
+    """The compressed walk (64-byte nodes, csrc/wide_bvh.cu) may only change WHICH inner nodes are visited, never a
+    hit: every decoded child box must contain the exact child box of the 4-wide node (supersets only add visits),
+    every decoded coordinate must be exactly representable in binary32, empty slots must decode to inverted boxes,
+    the child refs must be the 4-wide node's, and the boxes tested at the leaves must be the reference's own leaf
+    boxes bit for bit (Culling.hs:33,52; AABBs.hs:42-43)."""
+    sc, cam = SMALL[name]()
+    s = api.Scene(sc)
+    _, nodes, _, root, _ = s.download_bvh()
+    wide = s.download_wide()
+    cw, leaf_box, multi_box = s.download_compressed()
+    s.close()
+    assert len(cw) == len(wide) > 0
+    assert np.array_equal(cw[:, 12:16], wide[:, 24:28].view(np.uint32))
+    lo, hi = _decode_compressed(cw)
+    n = wide[:, 28].view(np.uint32)
+    for k in range(4):
+        live = n > k
+        exact_lo = np.stack([wide[:, 4 * k], wide[:, 4 * k + 1], wide[:, 16 + 2 * k]], axis=1).astype(np.float64)
+        exact_hi = np.stack([wide[:, 4 * k + 2], wide[:, 4 * k + 3], wide[:, 16 + 2 * k + 1]], axis=1).astype(np.float64)
+        assert (lo[live, k] <= exact_lo[live]).all() and (hi[live, k] >= exact_hi[live]).all()
+        assert (lo[~live, k] > hi[~live, k]).all()                   # empty slot: inverted on every axis
+        # the grid is tight: a decoded side is less than two grid steps away from the exact one
+        eb = cw[:, 3]
+        step = np.stack([(((eb >> (8 * d)) & 0xFF).astype(np.uint32) << 23).view(np.float32) for d in range(3)], axis=1)
+        assert ((exact_lo[live] - lo[live, k]) < 2 * step[live]).all() and ((hi[live, k] - exact_hi[live]) < 2 * step[live]).all()
+    _, bbox = _binary_leaf_sequence(nodes, root)
+    assert len(bbox) > 0
+    for ref, box in bbox.items():
+        src = multi_box if (ref & 0xC0000000) == 0xC0000000 else leaf_box
+        got = src[ref & 0x3FFFFFFF]
+        want = np.array([box[0], box[1], box[2], box[3], box[4], box[5]], np.float32)
+        assert np.array_equal(got[:6].view(np.uint32), want.view(np.uint32)), "leaf %x" % ref
 
 
 @pytest.mark.parametrize("depth", [0, 2, 3])
@@ -563,6 +629,9 @@ def test_full_size_c4_soup_sampled_oracle():
     assert torch.equal(ap, bp) and torch.equal(a.view(torch.int32), b.view(torch.int32))
     s.render_device(cam, b.data_ptr(), bp.data_ptr(), kernel=2, tune=0x4000)         # 4-wide tree pinned
     assert torch.equal(ap, bp) and torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for tune in (0x40000000, 0x80000000 - 2 ** 32):                                  # compressed / exact wide nodes pinned
+        s.render_device(cam, b.data_ptr(), bp.data_ptr(), kernel=2, tune=tune)
+        assert torch.equal(ap, bp) and torch.equal(a.view(torch.int32), b.view(torch.int32))
     s.close()
     assert st["n_primary"] == w * h
     orgb, opid, sel = _sampled_oracle(sc, cam, 1, 0, 256, 17)

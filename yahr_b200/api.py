@@ -344,6 +344,19 @@ class Scene:
         _check(L.yahr_b200_scene_download_wide(self._h, wide.ctypes.data))
         return wide
 
+    def download_compressed(self):
+        """(cwide[n_wide, 16] uint32 raw, leaf_box[n_prims, 8] float32, multi_box[n_multi, 8] float32): the compressed
+        wide nodes and the exact leaf boxes of the compressed walk (csrc/wide_bvh.cu)."""
+        i = self.info()
+        cw = np.zeros((i["n_wide_nodes"], 16), np.uint32)
+        lb = np.zeros((i["n_primitives"], 8), np.float32)
+        mb = np.zeros((i["n_multi_leaves"], 8), np.float32)
+        L = lib()
+        L.yahr_b200_scene_download_compressed.restype = C.c_int
+        L.yahr_b200_scene_download_compressed.argtypes = [C.c_void_p] * 4
+        _check(L.yahr_b200_scene_download_compressed(self._h, cw.ctypes.data, lb.ctypes.data, mb.ctypes.data))
+        return cw, lb, mb
+
     def render_rgb8(self, cam, recursion_depth=1, spp=1, seed=0, out=None):
         """yahr_b200_render_rgb8: the frame with the reference's 8-bit output stage applied on the GPU."""
         c = make_camera(cam)

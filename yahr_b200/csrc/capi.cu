@@ -105,6 +105,8 @@ struct yahr_scene {
   DeviceScene dev{};
   float4* d_nodes = nullptr;
   float4* d_wide = nullptr;              // 4-wide collapse of d_nodes (NULL: the root is a leaf, or not built)
+  float4 *d_cwide = nullptr, *d_leafBox = nullptr, *d_multiBox = nullptr;   // compressed copy of d_wide + exact leaf boxes
+  int preferCompressed = 0;              // per-scene choice: walk the compressed nodes by default
   float4* d_prims = nullptr;
   float4* d_normals = nullptr;
   uint2* d_multi = nullptr;
@@ -152,6 +154,7 @@ struct yahr_scene {
   std::map<std::tuple<int, int, int, int, int>, HostStrategy> hostStrategy;
 
   ~yahr_scene() {
+    cudaFree(d_cwide); cudaFree(d_leafBox); cudaFree(d_multiBox);
     cudaFree(d_nodes); cudaFree(d_wide); cudaFree(d_prims); cudaFree(d_normals); cudaFree(d_multi); cudaFree(d_materials);
     cudaFree(d_lights); cudaFree(d_areaLights); cudaFree(d_counters); cudaFree(d_order); cudaFree(d_rgb); cudaFree(d_primid); cudaFree(d_rgb8);
     for (auto& kv : tiles) {
@@ -376,6 +379,8 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     // the walk: bit 10 set = binary tree, bit 14 set = its 4-wide collapse, neither = the scene's own choice (attachWideTree)
     W.wideTree = (tune & 0x400u) ? 0u : ((tune & 0x4000u) ? 1u : (sc->preferBinary ? 0u : 1u));
     W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
+    // bit 30: the compressed 64-byte wide nodes, bit 31: the exact 128-byte ones, neither: the scene's own choice
+    W.compressed = (tune & 0x80000000u) ? 0u : ((tune & 0x40000000u) ? 1u : (sc->preferCompressed ? 1u : 0u));
     W.fused = (tune >> 12) & 3u;                   // bit 12 set = fused primary + shadow kernel (one light slot); 13: 72 registers
     // bit 15: one light slot -> ONE persistent kernel with committed probe chunks (k_wf_persist); bit 29 = the two-kernel set
     static const int envPersist = getenv("YAHR_B200_PERSIST") ? atoi(getenv("YAHR_B200_PERSIST")) : -1;
@@ -492,6 +497,16 @@ void attachWideTree(yahr_scene* sc) {
     sc->dev.wide = wo.wide;
     sc->info.n_wide_nodes = wo.nWide;
     sc->info.device_bytes += (uint64_t)wo.nWide * kWideNodeVec * sizeof(float4);
+    if (!getenv("YAHR_B200_NO_COMPRESSED")) {
+      CompressedWideOutput co;
+      if (!compressWideOnDevice(wo.wide, wo.nWide, sc->info.n_primitives, sc->info.n_multi_leaves, co))
+        throw CudaFailure{co.error, co.where, __FILE__, __LINE__};
+      if (co.nodes) {
+        sc->d_cwide = co.nodes; sc->d_leafBox = co.leafBox; sc->d_multiBox = co.multiBox;
+        sc->dev.cwide = co.nodes; sc->dev.leafBox = co.leafBox; sc->dev.multiBox = co.multiBox;
+        sc->info.device_bytes += co.bytes;
+      }
+    }
   } else {
     cudaFree(wo.wide);
   }
@@ -831,6 +846,23 @@ int yahr_b200_scene_download_wide(const yahr_scene* scene, float* wide_out) {
     if (scene->info.n_wide_nodes)
       CU(cudaMemcpy(wide_out, scene->d_wide, (size_t)scene->info.n_wide_nodes * kWideNodeVec * sizeof(float4),
                     cudaMemcpyDeviceToHost));
+    return YAHR_OK;
+  } catch (const CudaFailure& f) {
+    return cudaFail(f);
+  }
+}
+
+int yahr_b200_scene_download_compressed(const yahr_scene* scene, float* cwide_out, float* leaf_box_out, float* multi_box_out) {
+  if (!scene) return fail(YAHR_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!scene->d_cwide) return fail(YAHR_ERR_INVALID_ARGUMENT, "the scene has no compressed wide nodes");
+  try {
+    const yahr_scene_info& i = scene->info;
+    if (cwide_out && i.n_wide_nodes)
+      CU(cudaMemcpy(cwide_out, scene->d_cwide, (size_t)i.n_wide_nodes * 4 * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (leaf_box_out && i.n_primitives)
+      CU(cudaMemcpy(leaf_box_out, scene->d_leafBox, (size_t)i.n_primitives * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (multi_box_out && i.n_multi_leaves)
+      CU(cudaMemcpy(multi_box_out, scene->d_multiBox, (size_t)i.n_multi_leaves * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
     return YAHR_OK;
   } catch (const CudaFailure& f) {
     return cudaFail(f);

@@ -32,6 +32,9 @@ namespace yb {
 struct DeviceScene {
   const float4* nodes;
   const float4* wide;
+  const float4* cwide;      // compressed copy of `wide` (64 B per node, wide_bvh.cu) or NULL
+  const float4* leafBox;    // exact boxes of the single-primitive leaves, by DFS position (compressed walk)
+  const float4* multiBox;   // exact boxes of the multi-leaves
   const float4* prims;
   const float4* normals;
   const uint2* multiLeaves;
@@ -88,6 +91,7 @@ struct WavefrontParams {
   uint32_t capRegisters;      // tuning: primary kernel compiled for 8 CTAs/SM (<= 64 registers)
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
+  uint32_t compressed;        // ... through its compressed 64-byte nodes (conservative inner boxes, exact leaf boxes)
   uint32_t leafRun;           // wide walk: consecutive pending leaves of a lane are tested in one leaf phase
   uint32_t fused;             // one light slot: k_wf_fused (each warp walks its own batch's shadow probes) instead of
                               // primary + shadow; bit 1: the 7-CTAs-per-SM build (72 registers)

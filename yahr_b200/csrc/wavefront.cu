@@ -285,12 +285,47 @@ __device__ __forceinline__ void wideChildTest(const float4& b, float zlo, float 
 // One wide-node visit: four child box tests; the first passing child (left-first order) is entered, the
 // later passing ones are pushed in reverse order with their entry distance (re-validated against the then
 // current tMax when popped, exactly like the binary walk).  Returns false when the walk is finished.
-template <int OCT, class STK>
+// Decodes child K of a compressed node (wide_bvh.cu, k_wide_compress): coordinate = fma(2^23 + q, step, origin'), exact.
+// PRMT builds the float 2^23 + q straight from the byte: 0x4B0000qq.
+template <int K>
+__device__ __forceinline__ void decodeChild(const float4& v1, const float4& v2, float2 stepXy, float2 stepZz, float2 orgXy,
+                                            float2 orgZz, float4& b, float& zlo, float& zhi) {
+  constexpr unsigned sel = 0x7540u | (unsigned)K;
+  const float lox = __uint_as_float(__byte_perm(__float_as_uint(v1.x), 0x4B000000u, sel));
+  const float loy = __uint_as_float(__byte_perm(__float_as_uint(v1.y), 0x4B000000u, sel));
+  const float loz = __uint_as_float(__byte_perm(__float_as_uint(v1.z), 0x4B000000u, sel));
+  const float hix = __uint_as_float(__byte_perm(__float_as_uint(v1.w), 0x4B000000u, sel));
+  const float hiy = __uint_as_float(__byte_perm(__float_as_uint(v2.x), 0x4B000000u, sel));
+  const float hiz = __uint_as_float(__byte_perm(__float_as_uint(v2.y), 0x4B000000u, sel));
+  const float2 lo = __ffma2_rn(make_float2(lox, loy), stepXy, orgXy);
+  const float2 hi = __ffma2_rn(make_float2(hix, hiy), stepXy, orgXy);
+  const float2 zz = __ffma2_rn(make_float2(loz, hiz), stepZz, orgZz);
+  b = make_float4(lo.x, lo.y, hi.x, hi.y);
+  zlo = zz.x; zhi = zz.y;
+}
+
+template <int OCT, class STK, bool CMP>
 __device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& rp, Trav& s, const STK& stack) {
   YB_CNT(s, kCntWide);
-  const float4* np = sc.wide + kWideNodeVec * (size_t)s.cur;
-  const float4 b0 = __ldg(np + 0), b1 = __ldg(np + 1), b2 = __ldg(np + 2), b3 = __ldg(np + 3);
-  const float4 z01 = __ldg(np + 4), z23 = __ldg(np + 5), rf = __ldg(np + 6);
+  float4 b0, b1, b2, b3, z01, z23, rf;
+  if (CMP) {
+    const float4* np = sc.cwide + 4 * (size_t)s.cur;
+    const float4 v0 = __ldg(np + 0), v1 = __ldg(np + 1), v2 = __ldg(np + 2);
+    rf = __ldg(np + 3);
+    const uint32_t eb = __float_as_uint(v0.w);
+    const float sx = __uint_as_float((eb & 0xFFu) << 23), sy = __uint_as_float((eb & 0xFF00u) << 15),
+                sz = __uint_as_float((eb & 0xFF0000u) << 7);
+    const float2 stepXy = make_float2(sx, sy), stepZz = make_float2(sz, sz);
+    const float2 orgXy = make_float2(v0.x, v0.y), orgZz = make_float2(v0.z, v0.z);
+    decodeChild<0>(v1, v2, stepXy, stepZz, orgXy, orgZz, b0, z01.x, z01.y);
+    decodeChild<1>(v1, v2, stepXy, stepZz, orgXy, orgZz, b1, z01.z, z01.w);
+    decodeChild<2>(v1, v2, stepXy, stepZz, orgXy, orgZz, b2, z23.x, z23.y);
+    decodeChild<3>(v1, v2, stepXy, stepZz, orgXy, orgZz, b3, z23.z, z23.w);
+  } else {
+    const float4* np = sc.wide + kWideNodeVec * (size_t)s.cur;
+    b0 = __ldg(np + 0); b1 = __ldg(np + 1); b2 = __ldg(np + 2); b3 = __ldg(np + 3);
+    z01 = __ldg(np + 4); z23 = __ldg(np + 5); rf = __ldg(np + 6);
+  }
   bool p0, p1, p2, p3;
   float k0, k1, k2, k3;
   wideChildTest<OCT>(b0, z01.x, z01.y, rp, s.tMax, p0, k0);
@@ -325,7 +360,7 @@ __device__ __forceinline__ bool wideStep(const DeviceScene& sc, const RayPack& r
 
 // Inner phase of the wide walk: wide-node steps until no lane has inner work or enough lanes hold a leaf.
 // Only this loop is specialised per octant; the leaf code exists once (traverseWarpWide).
-template <int OCT, class STK>
+template <int OCT, class STK, bool CMP>
 __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& rp, Trav& s, const STK& stack, bool& run,
                                           int leafThreshold) {
   for (;;) {
@@ -333,11 +368,21 @@ __device__ __forceinline__ void widePhase(const DeviceScene& sc, const RayPack& 
     const bool atInner = run && !atLeaf;
     if (!__any_sync(kFull, atInner)) break;
     if (__popc(__ballot_sync(kFull, atLeaf)) >= leafThreshold) break;
-    if (atInner) run = wideStep<OCT>(sc, rp, s, stack);
+    if (atInner) run = wideStep<OCT, STK, CMP>(sc, rp, s, stack);
   }
 }
 
-template <bool ANY_HIT, class STK>
+// Compressed walk: the leaf's EXACT box against the ray's current tMax -- the reference's wrapCollider test on entry to
+// the leaf (AABBs.hs:42-43) -- before its primitives are tested; the inner boxes on the way down were only supersets.
+// (Only rays with finite 1/u walk the wide tree, so min / max are plain.)
+__device__ __forceinline__ bool leafBoxPasses(const DeviceScene& sc, const Ray& r, const Trav& s) {
+  const float4* bp = ((s.cur & kDevRefMultiBits) == kDevRefMultiBits ? sc.multiBox : sc.leafBox) + 2 * (size_t)(s.cur & 0x3FFFFFFFu);
+  const float4 a = __ldg(bp + 0), b = __ldg(bp + 1);
+  float key;
+  return boxTest(a.x, a.y, a.z, a.w, b.x, b.y, r, s.tMax, key);
+}
+
+template <bool ANY_HIT, bool CMP = false, class STK>
 __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ray& r, Trav& s, const STK& stack, bool busy,
                                                  int leafThreshold, bool leafRun, bool anyRt = false,
                                                  bool octants = true) {
@@ -355,22 +400,25 @@ __device__ __forceinline__ void traverseWarpWide(const DeviceScene& sc, const Ra
     const RayPack rp = packRay(r);
     for (;;) {
       switch (oct) {
-        case 0: widePhase<0>(sc, rp, s, stack, run, leafThreshold); break;
-        case 1: widePhase<1>(sc, rp, s, stack, run, leafThreshold); break;
-        case 2: widePhase<2>(sc, rp, s, stack, run, leafThreshold); break;
-        case 3: widePhase<3>(sc, rp, s, stack, run, leafThreshold); break;
-        case 4: widePhase<4>(sc, rp, s, stack, run, leafThreshold); break;
-        case 5: widePhase<5>(sc, rp, s, stack, run, leafThreshold); break;
-        case 6: widePhase<6>(sc, rp, s, stack, run, leafThreshold); break;
-        case 7: widePhase<7>(sc, rp, s, stack, run, leafThreshold); break;
-        default: widePhase<-1>(sc, rp, s, stack, run, leafThreshold); break;
+        case 0: widePhase<0, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 1: widePhase<1, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 2: widePhase<2, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 3: widePhase<3, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 4: widePhase<4, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 5: widePhase<5, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 6: widePhase<6, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        case 7: widePhase<7, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
+        default: widePhase<-1, STK, CMP>(sc, rp, s, stack, run, leafThreshold); break;
       }
       // every running lane now holds a leaf, or enough of them do
       const bool atLeaf = run && (s.cur & kDevRefLeafBit);
       if (!__any_sync(kFull, atLeaf)) break;
       // a lane whose next pending subtree is again a leaf (siblings in one wide node) tests it right away
       if (atLeaf) {
-        do { run = leafStep<ANY_HIT, false>(sc, r, s, stack, anyRt); } while (leafRun && run && (s.cur & kDevRefLeafBit));
+        do {
+          if (CMP && !leafBoxPasses(sc, r, s)) run = popNext(s, stack);
+          else run = leafStep<ANY_HIT, false>(sc, r, s, stack, anyRt);
+        } while (leafRun && run && (s.cur & kDevRefLeafBit));
       }
     }
   }
@@ -629,7 +677,7 @@ __device__ __forceinline__ uint32_t shadowResult(const WavefrontParams& W, uint3
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, int MIN_BLOCKS, bool WIDE, bool AREA, int SH>
+template <bool ORDERED, int MIN_BLOCKS, bool WIDE, bool AREA, int SH, bool CMP = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_constant__ WavefrontParams W) {
   YB_STACK(SH);
   const unsigned lane = threadIdx.x & 31u;
@@ -655,7 +703,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
     }
-    if (WIDE) traverseWarpWide<false>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+    if (WIDE) traverseWarpWide<false, CMP>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<false, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     flushCounts(W, s, 0, valid && s.best != kNoHit);
     shadeAndEmit<AREA, false>(W, valid, item, (uint32_t)(W.base.width * v + u), v, r, s.tMax, s.best, lane, sLocal);
@@ -1153,7 +1201,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const
 #endif   // !YB_COUNT_WORK
 
 // ---------------------------------------------------------------------------------------------
-template <bool ORDERED, bool WIDE, int MIN_BLOCKS, int SH>
+template <bool ORDERED, bool WIDE, int MIN_BLOCKS, int SH, bool CMP = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_constant__ WavefrontParams W) {
   YB_STACK(SH);
   const unsigned lane = threadIdx.x & 31u;
@@ -1179,7 +1227,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_shadow(const __grid_cons
         busy = travBegin(W.base.sc, r, a.w, s);
       }
     }
-    if (WIDE) traverseWarpWide<true>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+    if (WIDE) traverseWarpWide<true, CMP>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
     else traverseWarp<true, ORDERED>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.packed != 0);
     flushCounts(W, s, 1, false);
     uint32_t row = 0;
@@ -1267,8 +1315,9 @@ static void launchPersistent(void (*kernel)(WavefrontParams), const WavefrontPar
   kernel<<<numSMs * perSM, 128, 0, stream>>>(W);
 }
 
-// kernel<..., SH> for the run-time choice of shared-memory stack entries per lane (0, 8, 12)
-#define YB_PICK_SH(sh, K0, K8, K12) ((sh) >= 12u ? (K12) : ((sh) >= 8u ? (K8) : (K0)))
+// kernel<..., SH> for the run-time choice of shared-memory stack entries per lane: 0 (default) or 12 (kept so that the
+// negative result of profiles/r2a stays reproducible)
+#define YB_PICK_SH(sh, K0, K12) ((sh) >= 8u ? (K12) : (K0))
 
 #ifdef YB_COUNT_WORK
 cudaError_t launchWavefrontCounted(WavefrontParams W, int numSMs, cudaStream_t stream, uint32_t* launches,
@@ -1293,6 +1342,8 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     const bool wide = W.wideTree && !ordered && W.base.sc.wide != nullptr;
     // AREA: the scene has area lights (extension); kept out of the default instantiation
     const bool area = W.base.sc.nAreaLights != 0;
+    // the compressed 64-byte nodes (two-kernel set without area lights; the per-batch kernels keep the exact nodes)
+    const bool cmp = wide && !area && W.compressed && W.base.sc.cwide != nullptr;
     auto tail = [&]() {
       if (W.base.spp > 1) { k_wf_accum<<<itemBlocks, 256, 0, stream>>>(W); if (launches) *launches += 1; }
       k_wf_count<<<1, 1, 0, stream>>>(W);
@@ -1314,8 +1365,7 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
 #endif
     const bool oneSlot = wide && !area && !W.dense && W.base.sc.nSlots <= 1u;
     if (oneSlot && W.persist) {
-      launchPersistent(YB_PICK_SH(sh, (k_wf_persist<8, 0>), (k_wf_persist<8, 8>), (k_wf_persist<8, 12>)), W, numSMs, stream,
-                       16);                                         // the rings in q0 / q2 are sized for 16 CTAs per SM
+      launchPersistent(k_wf_persist<8, 0>, W, numSMs, stream, 16);  // the rings in q0 / q2 are sized for 16 CTAs per SM
       singleKernelEvents();
       tail();
       continue;
@@ -1333,9 +1383,10 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
       launchPersistent(wide ? k_wf_primary<false, 8, true, true, 0>
                             : (ordered ? k_wf_primary<true, 8, false, true, 0> : k_wf_primary<false, 8, false, true, 0>),
                        W, numSMs, stream);
+    else if (wide && cmp)
+      launchPersistent(k_wf_primary<false, 8, true, false, 0, true>, W, numSMs, stream);
     else if (wide)
-      launchPersistent(W.capRegisters ? YB_PICK_SH(sh, (k_wf_primary<false, 8, true, false, 0>), (k_wf_primary<false, 8, true, false, 8>),
-                                                   (k_wf_primary<false, 8, true, false, 12>))
+      launchPersistent(W.capRegisters ? YB_PICK_SH(sh, (k_wf_primary<false, 8, true, false, 0>), (k_wf_primary<false, 8, true, false, 12>))
                                       : k_wf_primary<false, 1, true, false, 0>, W, numSMs, stream);
     else
       launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false, false, 0> : k_wf_primary<false, 8, false, false, 0>)
@@ -1344,8 +1395,8 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
     if (timed) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
     // 10 CTAs / SM (48 registers) measured 2-3 % faster than the unconstrained 56 registers / 9 CTAs
-    if (wide) launchPersistent(YB_PICK_SH(sh, (k_wf_shadow<false, true, 10, 0>), (k_wf_shadow<false, true, 10, 8>),
-                                          (k_wf_shadow<false, true, 10, 12>)), W, numSMs, stream);
+    if (wide && cmp) launchPersistent(k_wf_shadow<false, true, 10, 0, true>, W, numSMs, stream);
+    else if (wide) launchPersistent(YB_PICK_SH(sh, (k_wf_shadow<false, true, 10, 0>), (k_wf_shadow<false, true, 10, 12>)), W, numSMs, stream);
     else launchPersistent(ordered ? k_wf_shadow<true, false, 1, 0> : k_wf_shadow<false, false, 1, 0>, W, numSMs, stream);
     if (timed) cudaEventRecord(phaseEvents[3], stream);
     if (launches) *launches += 2;

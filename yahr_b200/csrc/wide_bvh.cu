@@ -130,6 +130,78 @@ __global__ void k_wide_need(const float4* wide, uint32_t nInner, const uint32_t*
   need[w] = m;
 }
 
+// COMPRESSED 4-wide nodes (64 B instead of 128 B: four 128-bit loads per visit instead of seven).
+//
+// Only the LEAF boxes have to be the reference's exact boxes: by the argument at the top of this file a node is entered
+// by the reference iff its own box passes at that moment, so an inner box may be ANY superset of the exact one -- a
+// superset only adds visits, and every visit ends in exact leaf tests.  A compressed node stores its child boxes on an
+// 8-bit grid over the node's own box: per axis a grid step 2^e and an origin that is a multiple of the step;
+// lo is rounded DOWN and hi UP to the grid, so the decoded box contains the exact one.  The decoded coordinate
+// origin + q * 2^e is an exactly representable float by construction (|origin / 2^e| <= 2^23 - 512, q <= 255), the
+// kernels evaluate it with one FMA as fma(2^23 + q, 2^e, origin - 2^23 * 2^e) -- exact operands, exact result, one
+// rounding of a representable value -- and then run the SAME slab arithmetic on it as on an exact box: monotone in the
+// box coordinates for a ray with finite 1/u, hence "exact child passes => decoded child passes" and the decoded entry
+// distance is <= the exact one (it is the key the pop re-validates).  Leaf children are tested against their EXACT box
+// (kept per DFS position in leafBox / per multi-leaf in multiBox) with the then-current tMax when the leaf is visited,
+// which is precisely the reference's wrapCollider test (AABBs.hs:42-43).
+//   node = 4 x float4: (origin' x y z, step exponents ex | ey << 8 | ez << 16) with origin' = origin - 2^23 * step,
+//          (lo.x[4] lo.y[4] lo.z[4] hi.x[4]) and (hi.y[4] hi.z[4] - -) as bytes, the four child refs.
+// A tree with a non-finite box coordinate, or an extent beyond 2^100, is not compressed (flag bad).
+__global__ void k_wide_compress(const float4* wide, uint32_t nWide, float4* cw, float4* leafBox, float4* multiBox,
+                                uint32_t* bad) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nWide) return;
+  const float4* np = wide + kWideNodeVec * (size_t)w;
+  const float4 z01 = np[4], z23 = np[5], rf = np[6];
+  const uint32_t n = __float_as_uint(np[7].x);
+  const uint32_t refs[4] = {__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w)};
+  float lo[4][3], hi[4][3];
+  for (int k = 0; k < 4; ++k) {
+    const float4 b = np[k];
+    lo[k][0] = b.x; lo[k][1] = b.y; hi[k][0] = b.z; hi[k][1] = b.w;
+  }
+  lo[0][2] = z01.x; hi[0][2] = z01.y; lo[1][2] = z01.z; hi[1][2] = z01.w;
+  lo[2][2] = z23.x; hi[2][2] = z23.y; lo[3][2] = z23.z; hi[3][2] = z23.w;
+  uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0}, eb[3];
+  float originp[3];
+  for (int d = 0; d < 3; ++d) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (uint32_t k = 0; k < n; ++k) { mn = fmin(mn, (double)lo[k][d]); mx = fmax(mx, (double)hi[k][d]); }
+    if (!(isfinite(mn) && isfinite(mx)) || !(mn <= mx)) { *bad = 1u; return; }
+    const double ext = mx - mn, mag = fmax(fabs(mn), fabs(mx));
+    int e = -126;
+    if (ext > 0.0) { int ee; frexp(ext / 254.0, &ee); e = max(e, ee); }            // 2^ee > ext / 254
+    if (mag > 0.0) { int em; frexp(mag / 8388096.0, &em); e = max(e, em); }          // |origin / step| <= 2^23 - 512
+    if (e > 100) { *bad = 1u; return; }
+    const double step = ldexp(1.0, e);
+    const double origin = floor(mn / step) * step;
+    eb[d] = (uint32_t)(e + 127);
+    originp[d] = (float)(origin - 8388608.0 * step);
+    for (uint32_t k = 0; k < 4; ++k) {
+      uint32_t a = 255u, b = 0u;                                   // empty slot: inverted box
+      if (k < n) {
+        a = (uint32_t)floor(((double)lo[k][d] - origin) / step);
+        b = (uint32_t)ceil(((double)hi[k][d] - origin) / step);
+        if (b > 255u || a > b) { *bad = 1u; return; }              // (cannot happen; guards the byte range)
+      }
+      qlo[d] |= a << (8u * k);
+      qhi[d] |= b << (8u * k);
+    }
+  }
+  float4* out = cw + 4 * (size_t)w;
+  out[0] = make_float4(originp[0], originp[1], originp[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16)));
+  out[1] = make_float4(__uint_as_float(qlo[0]), __uint_as_float(qlo[1]), __uint_as_float(qlo[2]), __uint_as_float(qhi[0]));
+  out[2] = make_float4(__uint_as_float(qhi[1]), __uint_as_float(qhi[2]), 0.0f, 0.0f);
+  out[3] = rf;
+  for (uint32_t k = 0; k < n; ++k) {                                // exact boxes of the leaf children
+    const uint32_t r = refs[k];
+    if (r == kDevRefNull || !(r & kDevRefLeafBit)) continue;
+    float4* dst = ((r & kDevRefMultiBits) == kDevRefMultiBits ? multiBox : leafBox) + 2 * (size_t)(r & 0x3FFFFFFFu);
+    dst[0] = make_float4(lo[k][0], lo[k][1], lo[k][2], hi[k][0]);
+    dst[1] = make_float4(hi[k][1], hi[k][2], 0.0f, 0.0f);
+  }
+}
+
 inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
@@ -145,6 +217,36 @@ inline unsigned blocks(size_t n, unsigned per = 256) { return (unsigned)((n + pe
       return false;                                                                         \
     }                                                                                       \
   } while (0)
+
+bool compressWideOnDevice(const float4* wide, uint32_t nWide, uint32_t nPrims, uint32_t nMulti, CompressedWideOutput& out) {
+  out = CompressedWideOutput();
+  if (!wide || nWide == 0) return true;
+  uint32_t* bad = nullptr;
+  auto failWith = [&](cudaError_t e, const char* where) {
+    out.error = e; out.where = where;
+    cudaFree(out.nodes); cudaFree(out.leafBox); cudaFree(out.multiBox); cudaFree(bad);
+    out.nodes = out.leafBox = out.multiBox = nullptr;
+    return false;
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&out.nodes, (size_t)nWide * 4 * sizeof(float4))) != cudaSuccess) return failWith(e, "cudaMalloc(cwide)");
+  if ((e = cudaMalloc(&out.leafBox, (size_t)(nPrims ? nPrims : 1) * 2 * sizeof(float4))) != cudaSuccess) return failWith(e, "cudaMalloc(leafBox)");
+  if ((e = cudaMalloc(&out.multiBox, (size_t)(nMulti ? nMulti : 1) * 2 * sizeof(float4))) != cudaSuccess) return failWith(e, "cudaMalloc(multiBox)");
+  if ((e = cudaMalloc(&bad, sizeof(uint32_t))) != cudaSuccess) return failWith(e, "cudaMalloc(flag)");
+  if ((e = cudaMemset(bad, 0, sizeof(uint32_t))) != cudaSuccess) return failWith(e, "cudaMemset(flag)");
+  k_wide_compress<<<blocks(nWide), 256>>>(wide, nWide, out.nodes, out.leafBox, out.multiBox, bad);
+  uint32_t flag = 0;
+  if ((e = cudaMemcpy(&flag, bad, sizeof(flag), cudaMemcpyDeviceToHost)) != cudaSuccess) return failWith(e, "k_wide_compress");
+  cudaFree(bad);
+  bad = nullptr;
+  if (flag) {                    // not compressible (non-finite or huge boxes): the scene keeps the exact 128-byte nodes
+    cudaFree(out.nodes); cudaFree(out.leafBox); cudaFree(out.multiBox);
+    out.nodes = out.leafBox = out.multiBox = nullptr;
+    return true;
+  }
+  out.bytes = (uint64_t)nWide * 64 + (uint64_t)nPrims * 32 + (uint64_t)nMulti * 32;
+  return true;
+}
 
 bool buildWideOnDevice(const float4* flat, uint32_t nInner, uint32_t binaryDepth, WideBuildOutput& out) {
   out = WideBuildOutput();
