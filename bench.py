@@ -342,41 +342,47 @@ def check_frames(R, sc, cam, args, trav, world, rank, barrier, host_frames):
 
 
 def extra_workloads(args, world, rank, barrier):
-    """C5 as BASELINE.json names it -- 10 M triangles, 3840x2160, 64 spp, point + quad area light, tiles sharded over the
-    GPUs -- device-resident `value` only, a few frames (one frame is ~1.5 G rays)."""
+    """The other BASELINE.json configs as they are named there, device-resident `value` only, a few frames each: C5 (10 M
+    triangles, 3840x2160, 64 spp, point + quad area light -- the config quoted for 8 GPUs; one frame is ~1.5 G rays),
+    C2 (bunny proxy, 1920x1080, 16 spp, point + area light), C3 (32^3 spheres, 2048x2048, 4 spp) and the soup half of
+    C4 (1 M random triangles, 3840x2160, 1 spp).  Tiles sharded over the GPUs like the headline workload."""
     import torch
     import torch.distributed as dist
     from yahr_b200.dist import TileShardedRenderer
-    sc, cam, desc = workload("c5-area")
-    spp = 64
-    R = TileShardedRenderer(sc, cam, mode=args.exchange)
-    st = R.stats_render(recursion_depth=1, spp=spp)
-    rays = torch.tensor([st["n_primary"] + st["n_shadow"] + st["n_secondary"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(rays)
-    R.render(recursion_depth=1, spp=spp)
-    barrier()
-    steps = max(1, args.extra_steps)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for i in range(steps):
+    out = []
+    for name, spp in (("c5-area", 64), ("c2-area", 16), ("c3", 4), ("c4-soup", 1)):
+        sc, cam, desc = workload(name)
+        R = TileShardedRenderer(sc, cam, mode=args.exchange)
+        st = R.stats_render(recursion_depth=1, spp=spp)
+        rays = torch.tensor([st["n_primary"] + st["n_shadow"] + st["n_secondary"]], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.barrier()
-        ev[i][0].record()
+            dist.all_reduce(rays)
         R.render(recursion_depth=1, spp=spp)
-        ev[i][1].record()
-    barrier()
-    ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    info = R.scene.info()
-    mode = R.mode
-    R.close()
-    m = float(ms.mean())
-    return [{"name": "c5-area", "workload": desc.replace("run with --spp 64", "64 spp"), "spp": spp, "n_gpus": world,
-             "steps": steps, "ms_per_step": m, "value": float(rays) / (m * 1e-3) / 1e6, "unit": UNIT,
-             "rays_per_frame": float(rays), "exchange": mode, "scene_bytes": int(info["device_bytes"]),
-             "bvh_build_ms": info["build_ms"], "scaling": "strong",
-             "note": "area lights and spp > 1 are extensions (no reference counterpart): parity against the repo's own oracle"}]
+        barrier()
+        steps = max(1, args.extra_steps)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            if world > 1:
+                dist.barrier()
+            ev[i][0].record()
+            R.render(recursion_depth=1, spp=spp)
+            ev[i][1].record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        info = R.scene.info()
+        mode = R.mode
+        R.close()
+        del R
+        m = float(ms.mean())
+        out.append({"name": name, "workload": desc.replace("run with --spp 64", "64 spp").replace("run with --spp 16", "16 spp"),
+                    "spp": spp, "n_gpus": world, "steps": steps, "ms_per_step": m, "value": float(rays) / (m * 1e-3) / 1e6,
+                    "unit": UNIT, "rays_per_frame": float(rays), "exchange": mode, "scene_bytes": int(info["device_bytes"]),
+                    "bvh_build_ms": info["build_ms"], "scaling": "strong",
+                    "note": ("area lights and spp > 1 are extensions (no reference counterpart): parity against the repo's own oracle"
+                             if (spp > 1 or "area" in name) else "the reference's own configuration (1 spp, point light)")})
+    return out
 
 
 def run_reference(args):

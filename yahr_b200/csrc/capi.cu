@@ -123,6 +123,8 @@ struct yahr_scene {
   // two slots so that consecutive bands of the host-buffer entry can be in flight on two streams
   float4 *wfQ0[2] = {nullptr, nullptr}, *wfQ1[2] = {nullptr, nullptr}, *wfQ2[2] = {nullptr, nullptr};
   unsigned char* wfVis[2] = {nullptr, nullptr};
+  uint2* wfHits[2] = {nullptr, nullptr};        // three-kernel set: hit records between k_wf_trace and k_wf_shade
+  size_t wfHitEntries[2] = {0, 0};
   size_t wfEntries[2] = {0, 0};
   unsigned long long* d_workStats = nullptr;    // counting build: 16 work counters
   int preferBinary = 0;                         // per-scene choice of the walk: 1 = binary tree, 0 = its 4-wide collapse
@@ -163,7 +165,7 @@ struct yahr_scene {
     }
     cudaFree(d_rowDone);
     if (h_rowFlags) cudaFreeHost(h_rowFlags);
-    for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); }
+    for (int k = 0; k < 2; ++k) { cudaFree(wfQ0[k]); cudaFree(wfQ1[k]); cudaFree(wfQ2[k]); cudaFree(wfVis[k]); cudaFree(wfHits[k]); }
     cudaFree(d_workStats);
     cudaFree(wfWork); cudaFree(wfSampleBuf); cudaFree(wfAccum); cudaFree(d_bandProbes);
     if (ev0) cudaEventDestroy(ev0);
@@ -262,6 +264,7 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, in
 // Defaults of the wavefront set, from the sweeps in profiles/ (r2): see DESIGN.md section 4.
 constexpr uint32_t kDefaultPersist = 0u;         // device-resident frames: 1 = k_wf_persist, 0 = k_wf_primary + k_wf_shadow
 constexpr uint32_t kDefaultStackShared = 0u;     // traversal-stack entries per lane in shared memory
+constexpr uint32_t kDefaultSplit = 0u;           // 1 = three-kernel set (trace / shade / shadow)
 
 // Everything a frame needs, validated once; tiles are then enqueued in one or several ranges.
 struct FramePlan {
@@ -385,6 +388,9 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     // bit 15: one light slot -> ONE persistent kernel with committed probe chunks (k_wf_persist); bit 29 = the two-kernel set
     static const int envPersist = getenv("YAHR_B200_PERSIST") ? atoi(getenv("YAHR_B200_PERSIST")) : -1;
     W.persist = (tune & 0x20000000u) ? 0u : ((tune & 0x8000u) ? 1u : (envPersist >= 0 ? (uint32_t)envPersist : kDefaultPersist));
+    // bit 28: the three-kernel set (k_wf_trace -> k_wf_shade -> k_wf_shadow) instead of k_wf_primary -> k_wf_shadow
+    static const int envSplit = getenv("YAHR_B200_SPLIT") ? atoi(getenv("YAHR_B200_SPLIT")) : -1;
+    W.split = (tune & 0x10000000u) ? 1u : (envSplit >= 0 ? (uint32_t)envSplit : kDefaultSplit);
     // bits 24-27: traversal-stack entries per lane in shared memory: 0 = default, 1 = none (all local), 8, 12
     static const int envSh = getenv("YAHR_B200_STACK_SH") ? atoi(getenv("YAHR_B200_STACK_SH")) : -1;
     const uint32_t shBits = (tune >> 24) & 0xFu;
@@ -416,6 +422,18 @@ void enqueueTiles(yahr_scene* sc, const FramePlan& plan, uint32_t first, uint32_
       CU(cudaMalloc(&sc->wfQ2[slot], entries * sizeof(float4)));
       CU(cudaMalloc(&sc->wfVis[slot], entries));
       sc->wfEntries[slot] = entries;
+    }
+    W.hits = nullptr;
+    if (W.split && plan.P.depth == 1) {
+      const size_t nItemsL = ts.hostStart[first + count] - ts.hostStart[first];
+      const size_t hitEntries = ((nItemsL + 31) & ~(size_t)31) * plan.samplesPerLaunch;
+      if (hitEntries > sc->wfHitEntries[slot]) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(sc->wfHits[slot]); sc->wfHits[slot] = nullptr; sc->wfHitEntries[slot] = 0;
+        CU(cudaMalloc(&sc->wfHits[slot], hitEntries * sizeof(uint2)));
+        sc->wfHitEntries[slot] = hitEntries;
+      }
+      W.hits = sc->wfHits[slot];
     }
     W.q0 = sc->wfQ0[slot]; W.q1 = sc->wfQ1[slot]; W.q2 = sc->wfQ2[slot];
     W.visibility = W.dense ? sc->wfVis[slot] : nullptr;

@@ -92,6 +92,8 @@ struct WavefrontParams {
   uint32_t packed;            // octant-specialised packed-f32x2 node step when a warp shares an octant
   uint32_t wideTree;          // traverse the 4-wide collapse of the tree (reference order only)
   uint32_t compressed;        // ... through its compressed 64-byte nodes (conservative inner boxes, exact leaf boxes)
+  uint32_t split;             // three-kernel set: k_wf_trace (closest-hit walk only) -> k_wf_shade -> k_wf_shadow
+  uint2* hits;                // split: per (sample of the launch, item) the hit's DFS position and t
   uint32_t leafRun;           // wide walk: consecutive pending leaves of a lane are tested in one leaf phase
   uint32_t fused;             // one light slot: k_wf_fused (each warp walks its own batch's shadow probes) instead of
                               // primary + shadow; bit 1: the 7-CTAs-per-SM build (72 registers)

@@ -710,6 +710,63 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_primary(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Three-kernel set (W.split): the closest-hit walk and the shading of k_wf_primary as two kernels.
+//   k_wf_trace : persistent warps, camera ray + closest-hit walk only; writes (DFS position, t) per item.  No shading
+//                code in the kernel: the hot instructions are the walk loops and the leaf test (the L1.5 instruction
+//                cache holds 32 KB; k_wf_primary is 67 KB of code and 1.2 of its 8 warps per scheduler wait for
+//                instructions, profiles/r2d), and 48 registers instead of 64 let 10 CTAs per SM be resident.
+//   k_wf_shade : one thread per item, full warps of straight-line code: regenerates the camera ray with the same
+//                instructions (same bits), then shadeAndEmit exactly as k_wf_primary does after its walk.
+// Same arithmetic, same queue, same k_wf_shadow afterwards: bit-identical frames.
+template <int MIN_BLOCKS, bool CMP>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_trace(const __grid_constant__ WavefrontParams W) {
+  YB_STACK(0);
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&W.work[0], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= W.itemsPadded * W.samplesPerLaunch) break;
+    const uint32_t sLocal = W.samplesPerLaunch > 1u ? base / W.itemsPadded : 0u;
+    const uint32_t item = base - sLocal * W.itemsPadded + lane;
+    const bool valid = item < W.nItems;
+    Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+    Trav s;
+    s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
+    YB_CNT_INIT(s);
+    bool busy = false;
+    if (valid) {
+      int u, v;
+      itemPixel(W, item, u, v);
+      r = itemRay(W, u, v, W.sample + sLocal);
+      busy = travBegin(W.base.sc, r, 1e6f, s);
+    }
+    traverseWarpWide<false, CMP>(W.base.sc, r, s, stack, busy, (int)W.leafThreshold, W.leafRun != 0);
+    flushCounts(W, s, 0, valid && s.best != kNoHit);
+    W.hits[base + lane] = make_uint2(s.best, __float_as_uint(s.tMax));
+  }
+}
+
+template <bool AREA>
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WavefrontParams W) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;              // (sample of the launch, padded item)
+  if (idx - lane >= W.itemsPadded * W.samplesPerLaunch) return;            // whole warps only: shadeAndEmit votes
+  const uint32_t sLocal = W.samplesPerLaunch > 1u ? idx / W.itemsPadded : 0u;
+  const uint32_t item = idx - sLocal * W.itemsPadded;
+  const bool valid = item < W.nItems;
+  int u = 0, v = 0;
+  Ray r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
+  uint2 h = make_uint2(kNoHit, 0u);
+  if (valid) {
+    itemPixel(W, item, u, v);
+    r = itemRay(W, u, v, W.sample + sLocal);
+    h = W.hits[idx];
+  }
+  shadeAndEmit<AREA, false>(W, valid, item, (uint32_t)(W.base.width * v + u), v, r, __uint_as_float(h.y), h.x, lane, sLocal);
+}
+
 #ifndef YB_COUNT_WORK
 // ---------------------------------------------------------------------------------------------
 // Fused variant for ONE light slot (the reference's configuration: one point light): the warp that traced and shaded
@@ -1379,7 +1436,15 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
       continue;
     }
 #endif
-    if (area)
+    if (wide && W.split && W.hits) {
+      if (cmp) launchPersistent(k_wf_trace<10, true>, W, numSMs, stream);
+      else launchPersistent(k_wf_trace<10, false>, W, numSMs, stream);
+      if (timed) cudaEventRecord(phaseEvents[1], stream);
+      const uint32_t threads = W.itemsPadded * W.samplesPerLaunch;
+      if (area) k_wf_shade<true><<<(threads + 127u) / 128u, 128, 0, stream>>>(W);
+      else k_wf_shade<false><<<(threads + 127u) / 128u, 128, 0, stream>>>(W);
+      if (launches) *launches += 1;
+    } else if (area)
       launchPersistent(wide ? k_wf_primary<false, 8, true, true, 0>
                             : (ordered ? k_wf_primary<true, 8, false, true, 0> : k_wf_primary<false, 8, false, true, 0>),
                        W, numSMs, stream);
@@ -1392,7 +1457,7 @@ cudaError_t launchWavefront(WavefrontParams W, int numSMs, cudaStream_t stream, 
       launchPersistent(W.capRegisters ? (ordered ? k_wf_primary<true, 8, false, false, 0> : k_wf_primary<false, 8, false, false, 0>)
                                       : (ordered ? k_wf_primary<true, 1, false, false, 0> : k_wf_primary<false, 1, false, false, 0>),
                        W, numSMs, stream);
-    if (timed) cudaEventRecord(phaseEvents[1], stream);
+    if (timed && !(wide && W.split && W.hits)) cudaEventRecord(phaseEvents[1], stream);
     if (timed) cudaEventRecord(phaseEvents[2], stream);
     // 10 CTAs / SM (48 registers) measured 2-3 % faster than the unconstrained 56 registers / 9 CTAs
     if (wide && cmp) launchPersistent(k_wf_shadow<false, true, 10, 0, true>, W, numSMs, stream);

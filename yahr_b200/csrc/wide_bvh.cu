@@ -170,23 +170,37 @@ __global__ void k_wide_compress(const float4* wide, uint32_t nWide, float4* cw, 
     if (!(isfinite(mn) && isfinite(mx)) || !(mn <= mx)) { *bad = 1u; return; }
     const double ext = mx - mn, mag = fmax(fabs(mn), fabs(mx));
     int e = -126;
-    if (ext > 0.0) { int ee; frexp(ext / 254.0, &ee); e = max(e, ee); }            // 2^ee > ext / 254
+    if (ext > 0.0) { int ee; frexp(ext / 253.0, &ee); e = max(e, ee); }            // 2^ee > ext / 253
     if (mag > 0.0) { int em; frexp(mag / 8388096.0, &em); e = max(e, em); }          // |origin / step| <= 2^23 - 512
-    if (e > 100) { *bad = 1u; return; }
-    const double step = ldexp(1.0, e);
-    const double origin = floor(mn / step) * step;
-    eb[d] = (uint32_t)(e + 127);
-    originp[d] = (float)(origin - 8388608.0 * step);
-    for (uint32_t k = 0; k < 4; ++k) {
-      uint32_t a = 255u, b = 0u;                                   // empty slot: inverted box
-      if (k < n) {
-        a = (uint32_t)floor(((double)lo[k][d] - origin) / step);
-        b = (uint32_t)ceil(((double)hi[k][d] - origin) / step);
-        if (b > 255u || a > b) { *bad = 1u; return; }              // (cannot happen; guards the byte range)
+    bool done = false;
+    for (int attempt = 0; attempt < 4 && !done; ++attempt, ++e) {
+      if (e > 100) { *bad = 1u; return; }
+      const double step = ldexp(1.0, e);
+      const double origin = floor(mn / step) * step;                 // a multiple of the step, <= mn
+      uint32_t wl = 0, wh = 0;
+      bool fits = true;
+      for (uint32_t k = 0; k < 4 && fits; ++k) {
+        uint32_t a = 255u, b = 0u;                                   // empty slot: inverted box
+        if (k < n) {
+          // floor / ceil of (x - origin) / step; x - origin is NOT exact in binary64 when the magnitudes are far apart
+          // (x = 1e-16, origin = -8), so the candidates are corrected against the decoded values: origin + q * step IS
+          // exact (it is a binary32 number), and so are the comparisons with the exact coordinates
+          double qa = floor(((double)lo[k][d] - origin) / step), qb = ceil(((double)hi[k][d] - origin) / step);
+          while (origin + qa * step > (double)lo[k][d]) qa -= 1.0;
+          while (origin + qb * step < (double)hi[k][d]) qb += 1.0;
+          if (qa < 0.0 || qb > 255.0 || qa > qb) { fits = false; break; }
+          a = (uint32_t)qa; b = (uint32_t)qb;
+        }
+        wl |= a << (8u * k);
+        wh |= b << (8u * k);
       }
-      qlo[d] |= a << (8u * k);
-      qhi[d] |= b << (8u * k);
+      if (!fits) continue;                                           // one grid step too fine: double it
+      qlo[d] = wl; qhi[d] = wh;
+      eb[d] = (uint32_t)(e + 127);
+      originp[d] = (float)(origin - 8388608.0 * step);
+      done = true;
     }
+    if (!done) { *bad = 1u; return; }
   }
   float4* out = cw + 4 * (size_t)w;
   out[0] = make_float4(originp[0], originp[1], originp[2], __uint_as_float(eb[0] | (eb[1] << 8) | (eb[2] << 16)));
