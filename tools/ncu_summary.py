@@ -79,7 +79,11 @@ def main():
             "l1_lsu_wavefronts_pct": f(d, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
             "warps_active_pct": f(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "inst_executed": f(d, "smsp__inst_executed.sum"),
-            "l1_lsu_wavefronts": f(d, "l1tex__data_pipe_lsu_wavefronts.sum"),
+            # `--set full` carries the per-SM average, a `--metrics` pass the sum
+            "l1_lsu_wavefronts": (f(d, "l1tex__data_pipe_lsu_wavefronts.sum")
+                                  if "l1tex__data_pipe_lsu_wavefronts.sum" in col else
+                                  ((f(d, "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg") or 0.0)
+                                   * (f(d, "device__attribute_multiprocessor_count") or 148.0) or None)),
             "grid": f(d, "launch__grid_size"), "registers": f(d, "launch__registers_per_thread"),
             "local_sectors": (f(d, "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum") or 0)
             + (f(d, "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum") or 0),
