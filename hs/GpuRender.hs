@@ -46,6 +46,10 @@ foreign import ccall safe "yahr_b200_scene_destroy"
 foreign import ccall safe "yahr_b200_render"
   c_render :: Ptr YahrScene -> Ptr () -> CInt -> CInt -> Word64
            -> Ptr Float -> Ptr Word32 -> Ptr () -> IO CInt
+-- The same frame with JuicyPixels' ImageRGBF -> RGB8 conversion of savePngImage (main.hs:142) applied on the GPU:
+-- the buffer is an `Image PixelRGB8` payload (row-major, RGB interleaved), a quarter of the bytes cross PCIe.
+foreign import ccall safe "yahr_b200_render_rgb8"
+  c_render_rgb8 :: Ptr YahrScene -> Ptr () -> CInt -> CInt -> Word64 -> Ptr Word8 -> Ptr () -> IO CInt
 foreign import ccall unsafe "yahr_b200_last_error"
   c_last_error :: IO CString
 
