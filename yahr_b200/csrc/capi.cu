@@ -265,6 +265,7 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, in
 constexpr uint32_t kDefaultPersist = 0u;         // device-resident frames: 1 = k_wf_persist, 0 = k_wf_primary + k_wf_shadow
 constexpr uint32_t kDefaultStackShared = 0u;     // traversal-stack entries per lane in shared memory
 constexpr uint32_t kDefaultSplit = 0u;           // 1 = three-kernel set (trace / shade / shadow)
+constexpr uint32_t kDefaultRgb8Kernel = 0u;      // streamed 8-bit rows: 0 = two-kernel set, 1 = k_wf_fused
 
 // Everything a frame needs, validated once; tiles are then enqueued in one or several ranges.
 struct FramePlan {
@@ -1064,9 +1065,12 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
   // every lit row completes in the shadow phase, after the whole primary trace)
   // k_wf_fused by default (C4 1.59 ms against 1.75 - 1.90 for k_wf_persist on a whole frame, profiles/r2c-r2e);
   // YAHR_B200_HOST_FUSED=3 selects k_wf_persist, 2 the 72-register build of k_wf_fused, 0 the two-kernel set
+  // The 8-bit frame streams from the TWO-kernel set: its rows only become final in the shadow phase, but 24.9 MB (C4)
+  // need 0.44 ms of copy and the shadow kernel alone runs 0.43 ms, while the faster kernels end the call earlier
+  // (profiles/r2o).
   {
     const char* f = getenv("YAHR_B200_HOST_FUSED");
-    const uint32_t k = f ? (uint32_t)atoi(f) & 3u : 1u;
+    const uint32_t k = f ? (uint32_t)atoi(f) & 3u : (rgb8_out && plan.P.depth == 1 ? kDefaultRgb8Kernel : 1u);
     plan.W.persist = (k == 3u && plan.P.depth == 1) ? 1u : 0u;
     plan.W.fused = k == 3u ? 1u : k;
   }
@@ -1237,8 +1241,8 @@ static int renderHost(yahr_scene* scene, const yahr_camera* cam, int recursion_d
       const char* env = getenv("YAHR_B200_HOST_STREAM");
       const uint32_t nRowsS = (uint32_t)ts.rowY.size();
       bool useStream = plan.wavefront && !plan.W.dense && !plan.W.twoSlot && spp == 1 && nRowsS >= 2 && ts.d_rowOfV;
-      // the 8-bit frame is written by the per-batch kernels only (k_wf_fused*: 4-wide tree, no area lights)
-      if (rgb8_out && !(scene->dev.wide && scene->dev.nAreaLights == 0 && !getenv("YAHR_B200_HOST_FUSED"))) useStream = false;
+      // the 8-bit frame is written by the one-slot kernels without area lights (4-wide tree)
+      if (rgb8_out && !(scene->dev.wide && scene->dev.nAreaLights == 0)) useStream = false;
       if (useStream && env) useStream = atoi(env) != 0;
       else if (useStream && getenv("YAHR_B200_HOST_MEASURE")) {
         strategy = &scene->hostStrategy[std::make_tuple(W_, H_, shardIndex, shardCount, primid_out ? 1 : (rgb8_out ? 2 : 0))];

@@ -551,8 +551,10 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     float* out = W.sampleOut + 3 * (size_t)outIndex;
     const bool firstSample = W.sample + sLocal == 0u;
     if (!hit) {
-      if (FUSED) storeFinal(W, outIndex, 0.0f, 0.0f, 0.0f);
-      else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; }     // Nothing -> Vec3 0 0 0
+      // Nothing -> Vec3 0 0 0.  Final for this pixel unless several slots add to it later (then the float frame it is);
+      // storeFinal writes the 8-bit frame instead when the 8-bit host entry streams its rows
+      if (FUSED || !(W.dense || W.twoSlot)) storeFinal(W, outIndex, 0.0f, 0.0f, 0.0f);
+      else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; }
       if (W.base.primid && firstSample) W.base.primid[pixel] = kNoHit;
     } else {
       surf = surfaceAt(sc, idx, r, tHit);
@@ -636,8 +638,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     const float qnan = __uint_as_float(0x7FFFFFFFu);
     const size_t index = (size_t)(sLocal * W.framePixels + pixel);
     const float x = (nanBits & 1u) ? qnan : 0.0f, y = (nanBits & 2u) ? qnan : 0.0f, z = (nanBits & 4u) ? qnan : 0.0f;
-    if (FUSED) storeFinal(W, index, x, y, z);
-    else { float* out = W.sampleOut + 3 * index; out[0] = x; out[1] = y; out[2] = z; }
+    storeFinal(W, index, x, y, z);
   }
   if (FUSED) { local->nanBits = nanBits; local->row = row; }
   else if (W.rowFlags) rowsSignal(W, row, valid && nEmit == 0u, lane);     // pixels that are final without a shadow probe
@@ -667,10 +668,8 @@ __device__ __forceinline__ uint32_t shadowResult(const WavefrontParams& W, uint3
   if (unoccluded) c = W.q2[entry];
   const uint32_t nanBits = __float_as_uint(c.w) & 7u;
   const float qnan = __uint_as_float(0x7FFFFFFFu);
-  float* out = W.sampleOut + 3 * (size_t)__float_as_uint(b.w);
-  out[0] = (nanBits & 1u) ? qnan : 0.0f + c.x;
-  out[1] = (nanBits & 2u) ? qnan : 0.0f + c.y;
-  out[2] = (nanBits & 4u) ? qnan : 0.0f + c.z;
+  storeFinal(W, (size_t)__float_as_uint(b.w), (nanBits & 1u) ? qnan : 0.0f + c.x, (nanBits & 2u) ? qnan : 0.0f + c.y,
+             (nanBits & 4u) ? qnan : 0.0f + c.z);
   return __float_as_uint(c.w) >> 3;              // the pixel's tile row (streamed host output)
 }
 
