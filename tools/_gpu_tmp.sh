@@ -1,13 +1,11 @@
 mkdir -p gpurun_out
-echo "# 8-bit rows from the two-kernel set (default)" > gpurun_out/r2o_rgb8_two_kernel.txt
-timeout 300 python tools/e2e_held_sweep.py c4-terrain 2>&1 | grep -E "6144" >> gpurun_out/r2o_rgb8_two_kernel.txt
-echo "# 8-bit rows from k_wf_fused (YAHR_B200_HOST_FUSED=1)" >> gpurun_out/r2o_rgb8_two_kernel.txt
-YAHR_B200_HOST_FUSED=1 timeout 300 python tools/e2e_held_sweep.py c4-terrain 2>&1 | grep -E "6144" >> gpurun_out/r2o_rgb8_two_kernel.txt
-for w in c2 c3; do
-echo "# $w: two-kernel / fused" >> gpurun_out/r2o_rgb8_two_kernel.txt
-timeout 300 python tools/e2e_held_sweep.py $w 2>&1 | grep -E "6144" >> gpurun_out/r2o_rgb8_two_kernel.txt
-YAHR_B200_HOST_FUSED=1 timeout 300 python tools/e2e_held_sweep.py $w 2>&1 | grep -E "6144" >> gpurun_out/r2o_rgb8_two_kernel.txt
-done
-timeout 300 python tools/sweep_r2.py --workloads c4-terrain,c2 --tunes 0 --shares 1 >> gpurun_out/r2o_rgb8_two_kernel.txt 2>&1
-cat gpurun_out/r2o_rgb8_two_kernel.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2o_pytest.log 2>&1; tail -3 gpurun_out/r2o_pytest.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2z2_bench.json 2> gpurun_out/r2z2_bench.err; echo "bench rc=$?"
+python - <<'P'
+import json
+j=json.loads(open('gpurun_out/r2z2_bench.json').read().strip().splitlines()[-1])
+r=j['roofline']
+print(j['value'], j['ms_per_step'], j['e2e']['ms_per_step'], j['e2e']['rgb8']['ms_per_step'])
+print({k:r[k] for k in ('bound','achieved','peak','unit','frac','traffic','counts_source','counts_refused')})
+print(j['frame_check'])
+for x in j['extra_workloads']: print(x['name'],x['spp'],round(x['ms_per_step'],3),round(x['value']))
+P
