@@ -238,7 +238,12 @@ def build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clocks, la
     mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
     share = rays_local / max(rays_total, 1.0)
     default_run = args.depth == 1 and args.spp == 1 and args.kernel == 0 and args.tune == 0 and args.traversal == "reference"
-    cap, why = ncu_capture(args.workload) if (wf and default_run) else (None, "not the default kernel set / configuration")
+    if wf and default_run and launches_per_step == 2:
+        # a frame (or a rank's share) of at most 2.5 M work items runs the per-batch kernel k_wf_fused; the committed
+        # capture is of the two-kernel set
+        cap, why = None, "this share runs k_wf_fused (<= 2.5 M work items per launch); no capture of it is committed"
+    else:
+        cap, why = ncu_capture(args.workload) if (wf and default_run) else (None, "not the default kernel set / configuration")
     kernels = {}
     if cap:
         for short, ms in (("k_wf_primary", ph[0]), ("k_wf_shadow", ph[2])):

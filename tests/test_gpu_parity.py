@@ -61,13 +61,21 @@ def gpu_render_modes(sc, cam, depth=1, spp=1, seed=0):
         d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
         d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
         st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
-                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x400)
+                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x400 | 0x20000000)
         outs["wavefront/binary"] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
+        # tuning bit 29: the TWO-kernel set pinned (small frames use the per-batch kernel k_wf_fused by default), and
+        # bit 12: k_wf_fused pinned
+        for key, tune in (("wavefront/two-kernel", 0x20000000), ("wavefront/fused", 0x1000)):
+            d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
+            d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
+            st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
+                                  stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=tune)
+            outs[key] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
         # tuning bit 30: the wavefront set on the COMPRESSED wide nodes (conservative inner boxes, exact leaf boxes)
         d_rgb = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda")
         d_pid = torch.full((h, w), 12345, dtype=torch.int32, device="cuda")
         st2 = s.render_device(cam, d_rgb.data_ptr(), d_pid.data_ptr(), recursion_depth=depth, spp=spp, seed=seed,
-                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x40000000)
+                              stream=torch.cuda.current_stream().cuda_stream, kernel=2, tune=0x40000000 | 0x20000000)
         outs["wavefront/compressed"] = (d_rgb.cpu().numpy(), d_pid.cpu().numpy().view(np.uint32), st2)
     outs["reference"] = outs["mega/reference"]
     outs["ordered"] = outs["mega/ordered"]
@@ -120,14 +128,15 @@ def test_parity_small_scenes(name):
     orgb, opid, _, ost = o.render(cam)
     o.close()
     outs = gpu_render_modes(sc, cam)
-    for mode in ("host", "mega/reference", "wavefront/reference", "wavefront/binary", "wavefront/compressed"):
+    for mode in ("host", "mega/reference", "wavefront/reference", "wavefront/binary", "wavefront/compressed",
+                 "wavefront/two-kernel", "wavefront/fused"):
         rgb, pid, st = outs[mode]
         compare(rgb, pid, orgb, opid, 1.0, "%s/%s" % (name, mode))
         assert st["n_primary"] == ost["n_primary"]
         assert st["n_shadow"] == ost["n_shadow"], "shadow-ray count differs from Integrators.hs:59 semantics"
         assert st["launches"] >= 1
     # the compressed walk visits a superset of inner nodes and the same leaves: frames and ray counts bit-identical
-    a, b = outs["wavefront/reference"], outs["wavefront/compressed"]
+    a, b = outs["wavefront/two-kernel"], outs["wavefront/compressed"]
     assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
     assert a[2]["n_shadow"] == b[2]["n_shadow"]
     for mode in ("mega/ordered", "wavefront/ordered"):

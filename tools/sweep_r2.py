@@ -3,7 +3,7 @@
 1/N share of a frame (strided tile rows), with a bit-equality check of every variant against the first.
   python tools/sweep_r2.py --workloads c4-terrain,c4-soup --tunes 0,0x8000 --shares 1,8 [--reps 5]
 Tuning word (opts.reserved[0], csrc/capi.cu planFrame): bit 10 binary tree, bit 14 4-wide tree, bit 15 k_wf_persist,
-bit 29 two-kernel set, bits 24-27 shared-memory stack entries (1 = none, 8, 12), bit 28 keep consumed queue lines in L2."""
+bit 29 two-kernel set pinned (tune 0 picks k_wf_fused for frames of <= 2.5 M work items), bit 12 k_wf_fused, bits 24-27 shared-memory stack entries (1 = none, 8, 12), bit 28 keep consumed queue lines in L2."""
 import argparse
 import os
 import sys

@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyahr_b200.so")
+# YAHR_B200_LIB: another build of the same library (experiments with compile-time variants); default: the in-tree build
+LIB_PATH = os.environ.get("YAHR_B200_LIB") or os.path.join(_HERE, "libyahr_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _f32p = C.POINTER(C.c_float)
@@ -81,6 +82,8 @@ def build_library(force=False):
             if f.endswith((".cu", ".cpp", ".hpp", ".cuh")) or f == "Makefile"]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "yahr_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if os.environ.get("YAHR_B200_LIB"):
+        return LIB_PATH                      # a hand-built variant: never rebuilt behind the caller's back
     if force or stale:
         subprocess.check_call(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC], stdout=subprocess.DEVNULL)
     return LIB_PATH

@@ -265,7 +265,7 @@ const TileSet& tilesFor(yahr_scene* sc, int w, int h, int stride, int offset, in
 constexpr uint32_t kDefaultPersist = 0u;         // device-resident frames: 1 = k_wf_persist, 0 = k_wf_primary + k_wf_shadow
 constexpr uint32_t kDefaultStackShared = 0u;     // traversal-stack entries per lane in shared memory
 constexpr uint32_t kDefaultSplit = 0u;           // 1 = three-kernel set (trace / shade / shadow)
-constexpr uint32_t kDefaultRgb8Kernel = 0u;      // streamed 8-bit rows: 0 = two-kernel set, 1 = k_wf_fused
+constexpr uint32_t kFusedMaxItems = 2500000u;    // one-slot frames up to this many work items per launch use k_wf_fused
 
 // Everything a frame needs, validated once; tiles are then enqueued in one or several ranges.
 struct FramePlan {
@@ -385,7 +385,14 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     W.leafRun = ((tune >> 11) & 1u) ^ 1u;          // default: on (bit 11 set = one leaf per leaf phase)
     // bit 30: the compressed 64-byte wide nodes, bit 31: the exact 128-byte ones, neither: the scene's own choice
     W.compressed = (tune & 0x80000000u) ? 0u : ((tune & 0x40000000u) ? 1u : (sc->preferCompressed ? 1u : 0u));
-    W.fused = (tune >> 12) & 3u;                   // bit 12 set = fused primary + shadow kernel (one light slot); 13: 72 registers
+    // bit 12 set = the per-batch kernel k_wf_fused (one light slot), 13: its 72-register build; bit 29 = the two-kernel set.
+    // Neither: by size.  A frame of up to kFusedMaxItems work items is dominated by the ramp-up and the tail of the
+    // persistent kernels, and one launch beats two (profiles/r2p: C1 0.059 -> 0.048 ms, C2 0.532 -> 0.463 ms, a 1/8 share of
+    // C4 0.354 -> 0.325 ms); above it the two-kernel set's compacted any-hit walks win (C3 1.01 vs 1.27 ms, soup 10.0 vs 11.1).
+    W.fused = (tune >> 12) & 3u;
+    if (!W.fused && !(tune & 0x20000000u) && opts->recursion_depth == 1 &&
+        (double)ts.nItems * plan.samplesPerLaunch <= (double)kFusedMaxItems)
+      W.fused = 1u;
     // bit 15: one light slot -> ONE persistent kernel with committed probe chunks (k_wf_persist); bit 29 = the two-kernel set
     static const int envPersist = getenv("YAHR_B200_PERSIST") ? atoi(getenv("YAHR_B200_PERSIST")) : -1;
     W.persist = (tune & 0x20000000u) ? 0u : ((tune & 0x8000u) ? 1u : (envPersist >= 0 ? (uint32_t)envPersist : kDefaultPersist));
@@ -1065,12 +1072,12 @@ static void renderStreamedRows(yahr_scene* scene, FramePlan& plan, float* rgb_ou
   // every lit row completes in the shadow phase, after the whole primary trace)
   // k_wf_fused by default (C4 1.59 ms against 1.75 - 1.90 for k_wf_persist on a whole frame, profiles/r2c-r2e);
   // YAHR_B200_HOST_FUSED=3 selects k_wf_persist, 2 the 72-register build of k_wf_fused, 0 the two-kernel set
-  // The 8-bit frame streams from the TWO-kernel set: its rows only become final in the shadow phase, but 24.9 MB (C4)
-  // need 0.44 ms of copy and the shadow kernel alone runs 0.43 ms, while the faster kernels end the call earlier
-  // (profiles/r2o).
+  // A large 8-bit frame streams from the TWO-kernel set: its rows only become final in the shadow phase, but 24.9 MB (C4)
+  // need 0.44 ms of copy and the shadow kernel alone runs 0.43 ms, so the faster kernels decide the call (profiles/r2o).
   {
     const char* f = getenv("YAHR_B200_HOST_FUSED");
-    const uint32_t k = f ? (uint32_t)atoi(f) & 3u : (rgb8_out && plan.P.depth == 1 ? kDefaultRgb8Kernel : 1u);
+    // (8-bit: by size like the device-resident frames -- plan.W.fused as planFrame set it; float: always per batch)
+    const uint32_t k = f ? (uint32_t)atoi(f) & 3u : (rgb8_out && plan.P.depth == 1 ? (plan.W.fused ? 1u : 0u) : 1u);
     plan.W.persist = (k == 3u && plan.P.depth == 1) ? 1u : 0u;
     plan.W.fused = k == 3u ? 1u : k;
   }

@@ -25,7 +25,15 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 __device__ __forceinline__ float rcp(float x) { return __fdiv_rn(1.0f, x); }
 __device__ __forceinline__ float lensq(V3 v) { return dot(v, v); }
 __device__ __forceinline__ float len(V3 v) { return __fsqrt_rn(dot(v, v)); }
-__device__ __forceinline__ V3 vnorm(V3 v) { return vscale(rcp(len(v)), v); }                         // norm
+__device__ __forceinline__ V3 vnormInline(V3 v) { return vscale(rcp(len(v)), v); }                   // norm
+// CALL = true: the helper is a CALL to one out-of-line copy instead of an inline expansion -- same instructions, same
+// bits.  The per-batch kernels (k_wf_fused*, k_wf_persist) use it for norm and BSDF.at: they keep warps of one SM in the
+// walk, the shading and the probe walk at once, their hot code overflows the 32 KB L1.5 instruction cache, and the ten
+// inline copies of norm and two of BSDF.at are what can be shared (C4 k_wf_fused 1.60 -> 1.47 ms, profiles/r2p).  The
+// two-kernel set and the megakernel keep the inline expansions (outlined they are 4 - 7 % slower).
+static __device__ __noinline__ V3 vnormCall(V3 v) { return vnormInline(v); }
+template <bool CALL = false>
+__device__ __forceinline__ V3 vnorm(V3 v) { return CALL ? vnormCall(v) : vnormInline(v); }
 // GHC class-default min/max on Float (SURVEY.md note N)
 __device__ __forceinline__ float hmin(float x, float y) { return x <= y ? x : y; }
 __device__ __forceinline__ float hmax(float x, float y) { return x <= y ? y : x; }
@@ -199,6 +207,7 @@ struct Surface {
 
 // DifferentialGeometry of the accepted hit: recomputes the winner's intermediate values with the
 // same instructions as hitPrimitive, hence the same bits (Shapes.hs:20-27, 46-55).
+template <bool CALL = false>
 __device__ __forceinline__ Surface surfaceAt(const DeviceScene& sc, uint32_t idx, const Ray& r, float t) {
   Surface s;
   const float4 A = __ldg(&sc.prims[3 * (size_t)idx + 0]);
@@ -221,13 +230,13 @@ __device__ __forceinline__ Surface surfaceAt(const DeviceScene& sc, uint32_t idx
     const V3 n1 = xyz(__ldg(&sc.normals[3 * (size_t)idx + 1]));
     const V3 n2 = xyz(__ldg(&sc.normals[3 * (size_t)idx + 2]));
     const V3 ns = vadd(vadd(vscale(b0, n0), vscale(b1, n1)), vscale(b2, n2));
-    const V3 ss = vnorm(e2);
-    const V3 ts = vnorm(cross(ss, ns));
+    const V3 ss = vnorm<CALL>(e2);
+    const V3 ts = vnorm<CALL>(cross(ss, ns));
     s.n = ns;
     s.dpdu = cross(ts, ns);
   } else {
     const V3 c = xyz(A);
-    const V3 n = vnorm(vsub(s.x, c));
+    const V3 n = vnorm<CALL>(vsub(s.x, c));
     s.n = n;
     s.dpdu = cross(n, mk(0.0f, 0.0f, 1.0f));
   }
@@ -248,10 +257,11 @@ __device__ __forceinline__ MaterialD loadMaterial(const DeviceScene& sc, uint32_
 
 // Shading frame (BSDF.hs:36-40)
 struct Frame { V3 sn, tn, nn; };
+template <bool CALL = false>
 __device__ __forceinline__ Frame makeFrame(const Surface& s) {
   Frame f;
   f.nn = s.n;
-  f.sn = vnorm(s.dpdu);
+  f.sn = vnorm<CALL>(s.dpdu);
   f.tn = cross(f.nn, f.sn);
   return f;
 }
@@ -259,12 +269,13 @@ __device__ __forceinline__ V3 toLocal(const Frame& f, V3 v) { return mk(dot(v, f
 
 // BSDF.at for Composite [Scaled diffuse Lambertian, Scaled specular (Blinn e)] (Shaders.hs:12-14,
 // BSDF.hs:12-46): (0 + diffuse * lambert) + specular * blinn, all in the local frame.
-__device__ __forceinline__ V3 bsdfAt(const MaterialD& m, const Frame& f, V3 iw, V3 ow) {
+template <bool CALL>
+__device__ __forceinline__ V3 bsdfAtBody(const MaterialD& m, const Frame& f, V3 iw, V3 ow) {
   const V3 i = toLocal(f, iw), o = toLocal(f, ow);
   float lam = 0.0f, bl = 0.0f;
   if (i.z > 0.0f && o.z > 0.0f) {
     lam = __fdiv_rn(1.0f, YB_PI);
-    const V3 h = vnorm(vadd(i, o));
+    const V3 h = vnorm<CALL>(vadd(i, o));
     const float cosThetaO = fabsf(o.z), cosThetaI = fabsf(i.z);
     const float cosThetaH = dot(i, h);
     const float oDotH = dot(o, h);
@@ -276,6 +287,11 @@ __device__ __forceinline__ V3 bsdfAt(const MaterialD& m, const Frame& f, V3 iw, 
   const V3 a = vmul(m.diffuse, mk(lam, lam, lam));
   const V3 b = vmul(m.specular, mk(bl, bl, bl));
   return vadd(vadd(mk(0.0f, 0.0f, 0.0f), a), b);
+}
+static __device__ __noinline__ V3 bsdfAtCall(const MaterialD& m, const Frame& f, V3 iw, V3 ow) { return bsdfAtBody<true>(m, f, iw, ow); }
+template <bool CALL = false>
+__device__ __forceinline__ V3 bsdfAt(const MaterialD& m, const Frame& f, V3 iw, V3 ow) {
+  return CALL ? bsdfAtCall(m, f, iw, ow) : bsdfAtBody<false>(m, f, iw, ow);
 }
 
 // Counter-based jitter for samples >= 1 (extension; sample 0 = the reference's ray).
@@ -368,6 +384,7 @@ __device__ __forceinline__ V3 directIllumination(const DeviceScene& sc, const Su
 }
 
 // computeInitialRay (Cameras.hs:83-86) with the `linear` summation order ((0 + a) + b) + c) + d.
+template <bool CALL = false>
 __device__ __forceinline__ Ray cameraRay(const RenderParams& P, float u, float v) {
   float p[3];
 #pragma unroll
@@ -380,7 +397,7 @@ __device__ __forceinline__ Ray cameraRay(const RenderParams& P, float u, float v
   }
   const V3 origin = mk(P.origin[0], P.origin[1], P.origin[2]);
   const V3 direction = vsub(mk(p[0], p[1], p[2]), origin);
-  return makeRay(origin, vnorm(direction));
+  return makeRay(origin, vnorm<CALL>(direction));
 }
 
 // radiance / vcast / vhit (Integrators.hs:22-43), recursion unrolled into a forward pass that

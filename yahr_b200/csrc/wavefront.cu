@@ -471,11 +471,12 @@ __device__ __forceinline__ void itemPixel(const WavefrontParams& W, uint32_t ite
   v = win.y + 4 * strip + rem % rows;
 }
 
+template <bool CALL = false>
 __device__ __forceinline__ Ray itemRay(const WavefrontParams& W, int u, int v, uint32_t sample) {
   const uint32_t pixel = (uint32_t)(W.base.width * v + u);
   const float fu = (float)u + sampleOffset(W.base.seed, pixel, sample, 0);
   const float fv = (float)v + sampleOffset(W.base.seed, pixel, sample, 1);
-  return cameraRay(W.base, fu, fv);
+  return cameraRay<CALL>(W.base, fu, fv);
 }
 
 // Streamed host output: the lanes with `done` have just stored the final value of a pixel of tile row `row`.  One atomic
@@ -557,14 +558,14 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
       else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; }
       if (W.base.primid && firstSample) W.base.primid[pixel] = kNoHit;
     } else {
-      surf = surfaceAt(sc, idx, r, tHit);
+      surf = surfaceAt<FUSED>(sc, idx, r, tHit);
       if (W.base.primid && firstSample) W.base.primid[pixel] = surf.primId;
       mat = loadMaterial(sc, surf.material);
-      fr = makeFrame(surf);
+      fr = makeFrame<FUSED>(surf);
       // ((n . r) @* f r) * rs with rs = vcast 0 = 0 (Integrators.hs:26,37,41-43): +-0, or NaN when the
       // weight is not finite.  Stored as the pixel's base value; the direct term is added to it.
       const V3 refl = vsub(r.d, vscale(2.0f * dot(r.d, surf.n), surf.n));
-      const V3 w = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
+      const V3 w = vscale(dot(surf.n, refl), bsdfAt<FUSED>(mat, fr, refl, wo));
       const V3 base = vadd(vmul(w, mk(0.0f, 0.0f, 0.0f)), mk(0.0f, 0.0f, 0.0f));     // +0, or NaN
       nanBits = (base.x != base.x ? 1u : 0u) | (base.y != base.y ? 2u : 0u) | (base.z != base.z ? 4u : 0u);
       // several slots: the base is stored now and k_wf_resolve adds to it.  One slot: every pixel is stored exactly
@@ -582,8 +583,8 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     V3 p0 = mk(0, 0, 0), dl = mk(0, 0, 0), contrib = mk(0, 0, 0);
     if (hit) {
       const V3 pointToLight = vsub(lightPos, surf.x);
-      const V3 lightDir = vnorm(pointToLight);
-      const V3 k = bsdfAt(mat, fr, lightDir, wo);
+      const V3 lightDir = vnorm<FUSED>(pointToLight);
+      const V3 k = bsdfAt<FUSED>(mat, fr, lightDir, wo);
       const float cosL = area ? -dot(lightDir, lightNormal) : 1.0f;
       if (lensq(k) > 0.0f && (!area || cosL > 0.0f)) {
         emit = true;
@@ -595,7 +596,7 @@ __device__ __forceinline__ void shadeAndEmit(const WavefrontParams& W, bool vali
     }
     if (FUSED) {                                   // one slot, probe stays in registers
       if (emit) {
-        local->origin = p0; local->dir = vnorm(dl); local->tMax = len(dl); local->contrib = contrib;
+        local->origin = p0; local->dir = vnorm<FUSED>(dl); local->tMax = len(dl); local->contrib = contrib;
         local->emit = true;
         ++nEmit;
       }
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused(const __grid_const
     bool busy = false;
     if (valid) {
       itemPixel(W, item, u, v);
-      r = itemRay(W, u, v, W.sample + sLocal);
+      r = itemRay<true>(W, u, v, W.sample + sLocal);
       busy = travBegin(W.base.sc, r, 1e6f, s);
     } else {
       r = makeRay(mk(0, 0, 0), mk(0, 0, 1));
@@ -948,7 +949,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
         // illuminationAtPoint's probe (Lights.hs:20-24) from its origin: direction and length as shadeAndEmit computes them
         const V3 p0 = mk(a.x, a.y, a.z);
         const V3 dl = vsub(xyz(__ldg(&sc.lights[0])), p0);
-        r = makeRay(p0, vnorm(dl));
+        r = makeRay(p0, vnorm<true>(dl));
         busy = travBegin(sc, r, len(dl), s);
       }
     } else {
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_persist(const __grid_con
       valid = item < W.nItems;
       if (valid) {
         itemPixel(W, item, u, v);
-        r = itemRay(W, u, v, W.sample + sLocal);
+        r = itemRay<true>(W, u, v, W.sample + sLocal);
         busy = travBegin(sc, r, 1e6f, s);
       }
     }
@@ -1048,25 +1049,25 @@ __device__ __forceinline__ void shadeLevel(const WavefrontParams& W, bool alive,
     if (alive && writeId && W.base.primid) W.base.primid[pixel] = kNoHit;
     return;
   }
-  const Surface surf = surfaceAt(sc, idx, r, tHit);
+  const Surface surf = surfaceAt<true>(sc, idx, r, tHit);
   if (writeId && W.base.primid) W.base.primid[pixel] = surf.primId;
   const MaterialD mat = loadMaterial(sc, surf.material);
-  const Frame fr = makeFrame(surf);
+  const Frame fr = makeFrame<true>(surf);
   const V3 wo = vneg(r.d);
   const V3 refl = vsub(r.d, vscale(2.0f * dot(r.d, surf.n), surf.n));          // reflectionDir
-  o.weight = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
+  o.weight = vscale(dot(surf.n, refl), bsdfAt<true>(mat, fr, refl, wo));
   o.nextOrigin = vadd(surf.x, vscale(0.001f, refl));
   o.nextDir = refl;
   // directIllumination / illuminationAtPoint for the one point light (same expressions as shadeAndEmit's slot)
   const V3 lightPos = xyz(__ldg(&sc.lights[0])), spectrum = xyz(__ldg(&sc.lights[1]));
   const V3 pointToLight = vsub(lightPos, surf.x);
-  const V3 lightDir = vnorm(pointToLight);
-  const V3 k = bsdfAt(mat, fr, lightDir, wo);
+  const V3 lightDir = vnorm<true>(pointToLight);
+  const V3 k = bsdfAt<true>(mat, fr, lightDir, wo);
   if (lensq(k) > 0.0f) {
     o.emit = true;
     o.probeOrigin = vadd(surf.x, vscale(0.001f, lightDir));
     const V3 dl = vsub(lightPos, o.probeOrigin);
-    o.probeDir = vnorm(dl);
+    o.probeDir = vnorm<true>(dl);
     o.probeTMax = len(dl);
     const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
     o.contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
@@ -1096,7 +1097,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth(const __grid
     bool busy = false;
     if (valid) {
       itemPixel(W, item, u, v);
-      r = itemRay(W, u, v, W.sample + sLocal);
+      r = itemRay<true>(W, u, v, W.sample + sLocal);
       busy = travBegin(W.base.sc, r, 1e6f, s);
     }
     const uint32_t pixel = (uint32_t)(W.base.width * v + u);
@@ -1175,7 +1176,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const
     bool busy = false;
     if (valid) {
       itemPixel(W, item, u, v);
-      r = itemRay(W, u, v, W.sample + sLocal);
+      r = itemRay<true>(W, u, v, W.sample + sLocal);
       busy = travBegin(sc, r, 1e6f, s);
     }
     const uint32_t pixel = (uint32_t)(W.base.width * v + u);
@@ -1205,25 +1206,25 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_wf_fused_depth_lights(const
       s.cur = 0; s.sp = 0; s.tMax = 0.0f; s.best = kNoHit;
       if (alive) {
         const Ray lr = makeRay(lo, ld);
-        const Surface surf = surfaceAt(sc, hitIdx, lr, hitT);
+        const Surface surf = surfaceAt<true>(sc, hitIdx, lr, hitT);
         const MaterialD mat = loadMaterial(sc, surf.material);
-        const Frame fr = makeFrame(surf);
+        const Frame fr = makeFrame<true>(surf);
         const V3 wo = vneg(ld);
         const V3 refl = vsub(ld, vscale(2.0f * dot(ld, surf.n), surf.n));          // reflectionDir
         if (phase == 0) {
           if (level == 0 && firstSample && W.base.primid) W.base.primid[pixel] = surf.primId;
-          weight[level] = vscale(dot(surf.n, refl), bsdfAt(mat, fr, refl, wo));
+          weight[level] = vscale(dot(surf.n, refl), bsdfAt<true>(mat, fr, refl, wo));
         }
         if (phase < nL) {
           const V3 lightPos = xyz(__ldg(&sc.lights[2 * phase + 0])), spectrum = xyz(__ldg(&sc.lights[2 * phase + 1]));
           const V3 pointToLight = vsub(lightPos, surf.x);
-          const V3 lightDir = vnorm(pointToLight);
-          const V3 k = bsdfAt(mat, fr, lightDir, wo);
+          const V3 lightDir = vnorm<true>(pointToLight);
+          const V3 k = bsdfAt<true>(mat, fr, lightDir, wo);
           if (lensq(k) > 0.0f) {
             emit = true;
             const V3 p0 = vadd(surf.x, vscale(0.001f, lightDir));
             const V3 dl = vsub(lightPos, p0);
-            r = makeRay(p0, vnorm(dl));
+            r = makeRay(p0, vnorm<true>(dl));
             busy = travBegin(sc, r, len(dl), s);
             const V3 intensity = vscale(rcp(lensq(pointToLight)), spectrum);
             contrib = vmul(vscale(fabsf(dot(lightDir, surf.n)), k), intensity);
