@@ -16,7 +16,7 @@ The only exchange is at the end of a frame -- the reference's `concat` of per-ti
   Both end with the flag fence (yahr_b200_flag_signal / yahr_b200_flags_wait): a sequence number per rank in rank 0's
   memory that rank 0's stream waits for -- no collective on the frame path (round 1 used a one-element NCCL
   all-reduce; fence="nccl" keeps it).
-  "auto"   (default) "p2p" up to 5 GPUs, "rows" from 6 (C4: 4 GPUs p2p 0.64 / rows 0.74 ms, 8 GPUs 0.65 / 0.49 ms).
+  "auto"   (default) "p2p" (C4, round 2: 0.86 / 0.56 / 0.43 ms at 2 / 4 / 8 GPUs; rows 1.00 / 0.63 / 0.47 ms).
   "reduce" every rank renders into a zeroed local full frame and the frames are summed onto rank 0
            with one NCCL reduce -- exact, because every pixel has exactly one owner and x + 0 = x.
            This is the plain-library baseline.
@@ -37,10 +37,11 @@ class TileShardedRenderer:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         if mode == "auto":
-            # peer stores overlap traversal but arrive at rank 0 as small writes and their volume ((G-1)/G of the frame,
-            # twice for lit pixels) does not shrink with G; bulk row pushes do, but run after the kernels.  Measured on C4:
-            # 4 GPUs p2p 0.64 / rows 0.74 ms, 8 GPUs p2p 0.65 / rows 0.49 ms.
-            mode = "rows" if self.world >= 6 else "p2p"
+            # Round 2: peer stores at every GPU count.  With the per-batch kernel on a rank's share (one launch, every
+            # pixel stored once, straight into rank 0's frame) and the flag fence, p2p measured 0.86 / 0.56 / 0.43 ms at
+            # 2 / 4 / 8 GPUs on C4 against 1.00 / 0.63 / 0.47 ms for the streamed row pushes (profiles/r2y, r2g).
+            # (Round 1, two kernels + NCCL fence: p2p 0.65 ms, rows 0.49 ms at 8 GPUs, hence "rows from 6".)
+            mode = "p2p"
         self.group = group
         self.cam = cam
         self.width, self.height = api.image_size(cam)
