@@ -44,7 +44,9 @@ def _load_bytes_per_ray():
 # this same command.  It supplies the per-frame COUNTS that do not depend on timing -- executed warp instructions, L1
 # data-pipe wavefronts, DRAM bytes -- and bench.py turns them into live fractions with the kernel durations and the SM
 # clock it measures itself.  A capture is only trusted when its source fingerprint is the current tree's.
-NCU_SUMMARIES = {"c4-terrain": "profiles/r2_ncu_full_default_c4terrain.json"}
+NCU_SUMMARIES = {"c4-terrain": "profiles/r2_ncu_full_default_c4terrain.json",
+                 # the per-batch kernel (frames / shares of <= 2.5 M work items), captured on a whole C4 frame
+                 "c4-terrain/fused": "profiles/r2_ncu_full_k_wf_fused_c4terrain.json"}
 
 
 def ncu_capture(workload_name):
@@ -66,8 +68,8 @@ def ncu_capture(workload_name):
         short = k["name"].replace("void ", "").split("<")[0].split("(")[0].split("::")[-1]
         if short in ("k_wf_primary", "k_wf_shadow", "k_wf_fused"):
             by[short] = k
-    if "k_wf_primary" not in by:
-        return None, "capture %s holds no k_wf_primary launch" % path
+    if "k_wf_primary" not in by and "k_wf_fused" not in by:
+        return None, "capture %s holds no k_wf_primary / k_wf_fused launch" % path
     return {"path": path, "fingerprint": fp, "kernels": by}, None
 
 
@@ -238,15 +240,15 @@ def build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clocks, la
     mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
     share = rays_local / max(rays_total, 1.0)
     default_run = args.depth == 1 and args.spp == 1 and args.kernel == 0 and args.tune == 0 and args.traversal == "reference"
-    if wf and default_run and launches_per_step == 2:
-        # a frame (or a rank's share) of at most 2.5 M work items runs the per-batch kernel k_wf_fused; the committed
-        # capture is of the two-kernel set
-        cap, why = None, "this share runs k_wf_fused (<= 2.5 M work items per launch); no capture of it is committed"
+    fused_run = wf and default_run and launches_per_step == 2
+    if fused_run:
+        # a frame (or a rank's share) of at most 2.5 M work items runs the per-batch kernel k_wf_fused: its own capture
+        cap, why = ncu_capture(args.workload + "/fused")
     else:
         cap, why = ncu_capture(args.workload) if (wf and default_run) else (None, "not the default kernel set / configuration")
     kernels = {}
     if cap:
-        for short, ms in (("k_wf_primary", ph[0]), ("k_wf_shadow", ph[2])):
+        for short, ms in ((("k_wf_fused", ph[0]),) if fused_run else (("k_wf_primary", ph[0]), ("k_wf_shadow", ph[2]))):
             k = cap["kernels"].get(short)
             if not k or ms <= 0:
                 continue
@@ -270,7 +272,7 @@ def build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clocks, la
                        "note": "SURVEY 8(d): every box / primitive fetch of every ray under the REFERENCE's traversal at "
                                "32 B per box; the scene is cache-resident and the 4-wide walk skips ancestor boxes, so "
                                "this is a work-rate figure, not an HBM fraction (it can exceed 1)"}
-    dom = kernels.get("k_wf_primary")
+    dom = kernels.get("k_wf_fused" if fused_run else "k_wf_primary")
     if dom:
         bound = "issue" if dom["issue_frac"] >= (dom["l1_frac"] or 0.0) else "l1"
         frac = dom["issue_frac"] if bound == "issue" else dom["l1_frac"]
@@ -281,7 +283,8 @@ def build_roofline(args, rays_local, rays_total, kernel_ms, phase_ms, clocks, la
     else:
         bound, frac, achieved, rpeak, unit, traffic = "issue", None, None, n_sm * 4.0 * mhz * 1e6 / 1e9, "G warp-inst/s", None
     return {"bound": bound, "achieved": achieved, "peak": rpeak, "unit": unit, "frac": frac, "traffic": traffic,
-            "kernel": "k_wf_primary (primary trace + shading, dominant); k_wf_shadow listed beside it" if wf else "k_render_mega",
+            "kernel": ("k_wf_fused (per-batch kernel: this share has <= 2.5 M work items)" if fused_run else
+                       "k_wf_primary (primary trace + shading, dominant); k_wf_shadow listed beside it") if wf else "k_render_mega",
             "kernel_ms": k_ms, "phase_ms": {"primary_trace_and_shade": ph[0], "shadow_trace": ph[2]} if wf else None,
             "peak_source": "%d SMs x %s per cycle x %.0f MHz (median SM clock sampled during this run)"
                            % (n_sm, "4 issue slots" if bound == "issue" else "1 L1 wavefront", mhz),
