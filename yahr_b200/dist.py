@@ -255,6 +255,13 @@ class SharedHostFrame:
             barrier()
         if not self._owner:
             self.shm = shared_memory.SharedMemory(name=name)
+            # only the owner unlinks the segment: keep this process's resource tracker from "cleaning it up" (and
+            # warning about it) at exit
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.array = np.ndarray((int(height), int(width), 3), np.float32, buffer=self.shm.buf)
         import torch
         rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
