@@ -470,13 +470,13 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         # the timed region lasts only a few milliseconds (nvidia-smi samples every 200 ms): keep the same load up for
-        # about 0.8 s more (at most 500 frames), untimed, so that the clock / throttle samples are taken under this very workload
+        # about 1.6 s more (at most 4000 frames), untimed, so that several clock / throttle samples are taken under this very workload
         # (the frame count is derived from the max-over-ranks step time, so it is the same on every rank: the exchange
         # contains a collective)
         probe = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ev]))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(probe, op=dist.ReduceOp.MAX)
-        extra = int(min(500, max(1, 800.0 / max(float(probe), 1e-3))))
+        extra = int(min(4000, max(1, 1600.0 / max(float(probe), 1e-3))))
         for k in range(extra):
             R.render(recursion_depth=args.depth, spp=args.spp, traversal=trav, kernel=args.kernel, tune=args.tune)
             if k % 20 == 19:
