@@ -164,3 +164,39 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"(from|import)\s+oracle|oracle/|yahr_oracle|liboracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_out_buffer_validation_is_strict():
+    """api._check_out guards every raw pointer handed to the C ABI: dtype, exact shape, C-contiguity, writeability."""
+    import numpy as np
+    api._check_out(np.zeros((4, 6, 3), np.float32), (4, 6, 3), np.float32, "rgb")
+    bad = [np.zeros((4, 6, 3), np.float64), np.zeros((6, 4, 3), np.float32), np.zeros((4, 12, 3), np.float32)[:, ::2],
+           np.zeros((4, 6, 3), np.float32).T, [[0.0] * 18] * 4]
+    ro = np.zeros((4, 6, 3), np.float32)
+    ro.setflags(write=False)
+    for a in bad + [ro]:
+        with pytest.raises(ValueError):
+            api._check_out(a, (4, 6, 3), np.float32, "rgb")
+
+
+def test_bench_refuses_a_stale_ncu_capture(monkeypatch):
+    """bench.py takes its per-launch instruction / wavefront counts from a committed ncu summary only when that summary
+    was taken on the sources the loaded library is built from (fingerprint of csrc/* + the header)."""
+    import json
+    import bench
+    path = os.path.join(ROOT, bench.NCU_SUMMARIES["c4-terrain"])
+    js = json.load(open(path))
+    assert len(js["fingerprint"]) == 16 and any("k_wf_primary" in k["name"] for k in js["kernels"])
+    monkeypatch.setattr(api, "source_fingerprint", lambda: js["fingerprint"])
+    cap, why = bench.ncu_capture("c4-terrain")
+    assert why is None and cap["kernels"]["k_wf_primary"]["inst_executed"] > 1e8
+    monkeypatch.setattr(api, "source_fingerprint", lambda: "0" * 16)
+    cap, why = bench.ncu_capture("c4-terrain")
+    assert cap is None and "refused" in why
+    cap, why = bench.ncu_capture("no-such-workload")
+    assert cap is None and why
+
+
+def test_source_fingerprint_tracks_the_kernel_sources():
+    fp = api.source_fingerprint()
+    assert len(fp) == 16 and fp == api.source_fingerprint()
