@@ -37,8 +37,14 @@ def main():
     if rank == 0:
         print("dist_check: world=%d backend=%s devices=%d%s" % (world, dist.get_backend(), torch.cuda.device_count(),
                                                                 " (all ranks on cuda:0)" if same_device else ""), flush=True)
+    # a third scene with TWO point lights: the compacted two-slot path, whose probes add to the pixel with float atomics --
+    # into rank 0's frame over NVLink in the p2p mode
+    two_sc, two_cam = scenes.c1_scene_yahrr(400, 300)
+    two_sc = dict(two_sc)
+    two_sc["lights"] = np.concatenate([np.asarray(two_sc["lights"], np.float32),
+                                       np.array([[-6.0, 8.0, 4.0, 300.0, 260.0, 220.0]], np.float32)])
     for name, (sc, cam) in {"bunny": scenes.c2_bunny_proxy(960, 540, nu=80, nv=60),
-                            "c1": scenes.c1_scene_yahrr(517, 389)}.items():
+                            "c1": scenes.c1_scene_yahrr(517, 389), "c1-two-lights": (two_sc, two_cam)}.items():
         w, h = api.image_size(cam)
         ref = None
         if rank == 0:
