@@ -365,11 +365,12 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     // light slots: 1 -> compacted queue, every pixel stored once; 2 -> compacted queue + float atomics (order-free for
     // two addends; YAHR_B200_NO_TWO_SLOT=1 keeps the dense path); 3 or more -> dense entries + in-order resolve
     // The atomics land in the per-sample frames of the launch; once those are far larger than L2 they cost more than the
-    // dense path's streaming resolve (measured, profiles/r2f: C2 + area light, 1920x1080, 16 samples per launch = 0.4 GB:
-    // 14.7 -> 12.9 ms; C5 + area light, 3840x2160, 16 per launch = 1.6 GB: 74.7 -> 77.1 ms), hence the size limit.
+    // dense path's streaming resolve (measured, profiles/r2f, r2aa: C2 + area light, 1920x1080, 16 samples per launch =
+    // 0.40 GB: 14.7 -> 12.9 ms; C5 + area light, 3840x2160, 6 per launch = 0.60 GB: 75 -> 77 ms at any number of samples
+    // per launch), hence the size limit.
     static const int envTwoSlot = getenv("YAHR_B200_TWO_SLOT") ? atoi(getenv("YAHR_B200_TWO_SLOT")) : -1;
     const double sampleFrameBytes = (double)px * plan.samplesPerLaunch * 12.0;
-    W.twoSlot = (nL == 2 && (envTwoSlot >= 0 ? envTwoSlot != 0 : sampleFrameBytes <= 0.8e9)) ? 1u : 0u;
+    W.twoSlot = (nL == 2 && (envTwoSlot >= 0 ? envTwoSlot != 0 : sampleFrameBytes <= 0.45e9)) ? 1u : 0u;
     W.tileStart = ts.d_tileStart; W.nItems = ts.nItems; W.itemBase = 0; W.sample = 0; W.dense = (nL > 1 && !W.twoSlot) ? 1u : 0u;
     W.itemPixels = ts.d_itemPixels;
     // tuning knobs (opts->reserved[0]): bits 0-7 leaf-parking threshold (0 = default), bits 16-23 CTAs/SM
