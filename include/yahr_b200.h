@@ -114,8 +114,9 @@ typedef struct yahr_render_opts {
   int32_t traversal;        /* YAHR_TRAVERSAL_* */
   int32_t tile_stride;      /* render tiles tile_offset, tile_offset + tile_stride, ... of the reference's */
   int32_t tile_offset;      /*   own squareBatches tiling (Sampling.hs:5-21); 1 / 0 = the whole image      */
-  int32_t kernel;           /* 0 = default kernel set; other values select experimental variants */
-  int32_t reserved[4];
+  int32_t kernel;           /* 0 = default kernel set; 1 = megakernel, 2 = wavefront kernels (experiments) */
+  int32_t reserved[4];      /* 0 = defaults.  [0]: tuning word of the wavefront kernels (experiments; DESIGN.md
+                               section 10), [1]: 1 = tile_stride / tile_offset count whole ROWS of the tile grid */
 } yahr_render_opts;
 
 typedef struct yahr_stats {

@@ -363,7 +363,7 @@ int planFrame(yahr_scene* sc, const yahr_camera* cam, const yahr_render_opts* op
     }
     W.base = P;
     // light slots: 1 -> compacted queue, every pixel stored once; 2 -> compacted queue + float atomics (order-free for
-    // two addends; YAHR_B200_NO_TWO_SLOT=1 keeps the dense path); 3 or more -> dense entries + in-order resolve
+    // two addends; YAHR_B200_TWO_SLOT=0 keeps the dense path); 3 or more -> dense entries + in-order resolve
     // The atomics land in the per-sample frames of the launch; once those are far larger than L2 they cost more than the
     // dense path's streaming resolve (measured, profiles/r2f, r2aa: C2 + area light, 1920x1080, 16 samples per launch =
     // 0.40 GB: 14.7 -> 12.9 ms; C5 + area light, 3840x2160, 6 per launch = 0.60 GB: 75 -> 77 ms at any number of samples

@@ -12,6 +12,12 @@
 //                  (several lights; k_wf_resolve then sums a pixel's lights in light order).
 //   k_wf_accum   : spp > 1 only (extension): one launch traces up to 16 samples of every pixel (sample-major
 //                  work items, per-sample frames); acc += sample in sample order, and the final divide.
+//   k_wf_fused   : ONE light slot, per batch: the warp that traced and shaded a batch walks its probes itself; the
+//                  default for frames / shares of <= 2.5 M work items and behind the streamed float host rows;
+//                  k_wf_fused_depth{,_lights} carry the same plan through the levels of Whitted recursion.
+//   Selectable, parity-tested, not default ("Round 2"): k_wf_persist (one launch per frame, probes
+//   through committed chunks in per-CTA rings), k_wf_trace + k_wf_shade (walk and shading as two kernels), the walk
+//   on compressed 64-byte nodes (template flag CMP), the first stack entries in shared memory (Stack<SH>).
 //
 // The walk is the reference's (left child first, box test on entry with the current tMax, later hit
 // replaces), by default on the 4-wide collapse of the tree (wide_bvh.cu: same leaves, same order, same

@@ -243,7 +243,7 @@ bool Parser::object(Obj& o) {
               if (peekIdent("Nothing")) { ++i; return true; }
               if (!ident("Just")) return false;
               o.hasSmooth = true;
-              return list([&] { bool b; if (!boolv(b)) return false; o.smooth.push_back(b ? 1 : 0); return true; });
+              return list([&] { bool b = false; if (!boolv(b)) return false; o.smooth.push_back(b ? 1 : 0); return true; });
             }) || !expect(','))
           return false;
       }
