@@ -1,11 +1,11 @@
-# Final multi-GPU evidence of a round on an 8-GPU box: bench at N = 8, 4, 2 (default exchange; p2p at 8 too), each line
+# Final multi-GPU evidence of a round on an 8-GPU box: bench at N = 8, 4, 2 (default exchange = p2p; the row pushes at 8 too), each line
 # with frame_check and extra_workloads, and the stand-alone frame-assembly check at N = 8.  Results in gpurun_out/ (r2y_*).
 mkdir -p gpurun_out
 run() { name=$1; n=$2; shift 2
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus $n --steps 20 --warmup 5 "$@" > gpurun_out/r2y_bench_$name.json 2> gpurun_out/r2y_bench_$name.err
   echo "bench $name rc=$?"; }
 run n8 8
-run n8_p2p 8 --exchange p2p --no-extra
+run n8_rows 8 --exchange rows --no-extra
 run n4 4
 run n2 2
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29552 tests/dist_check.py > gpurun_out/r2y_dist_check_n8.log 2>&1; echo "dist_check n8 rc=$?"
